@@ -1,0 +1,64 @@
+"""ctypes binding of libpss.so (C ABI declared in include/pss.h).
+
+The product path has NO CPU fallback: if the shared library is missing or does not load, importing
+this module raises, loudly.  Build it with `python __graft_entry__.py build` (nvcc, sm_100a).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpss.so")
+
+
+class PssError(RuntimeError):
+    pass
+
+
+class PsdOut(C.Structure):
+    _fields_ = [("db", C.c_void_p), ("cols", C.c_void_p), ("W", C.c_int), ("stats", C.c_void_p)]
+
+
+def _signatures():
+    vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
+    return {
+        "pss_init": (i32, [i32, C.POINTER(vp)]),
+        "pss_destroy": (None, [vp]),
+        "pss_strerror": (C.c_char_p, [i32]),
+        "pss_last_error": (C.c_char_p, [vp]),
+        "pss_version": (i32, []),
+        "pss_set_stream": (i32, [vp, vp]),
+        "pss_sync": (i32, [vp]),
+        "pss_kernel_launches": (i64, [vp]),
+        "pss_host_alloc": (vp, [C.c_size_t]),
+        "pss_host_free": (None, [vp]),
+        "pss_psd_c64": (i32, [vp, vp, i32, i64, i32, i32, i32, C.POINTER(PsdOut)]),
+        "pss_psd_c64_dev": (i32, [vp, vp, i32, i64, i32, i32, i32, C.POINTER(PsdOut)]),
+        "pss_scan_c64": (i32, [vp, vp, i32, i64, i32, f32, vp, vp, vp]),
+        "pss_scan_c64_dev": (i32, [vp, vp, i32, i64, i32, f32, vp, vp, vp]),
+    }
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise PssError(
+            f"{LIB_PATH} not found: the CUDA library is not built. Run `python __graft_entry__.py build` "
+            "(there is deliberately no numpy fallback in the product path).")
+    handle = C.CDLL(LIB_PATH)
+    sigs = _signatures()
+    for name, (res, args) in sigs.items():
+        fn = getattr(handle, name)       # AttributeError here = header/library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    return handle, sigs
+
+
+lib, SIGNATURES = _load()
+
+
+def check(ctx_handle, rc: int, what: str):
+    if rc != 0:
+        msg = lib.pss_strerror(rc).decode()
+        detail = lib.pss_last_error(ctx_handle).decode() if ctx_handle else ""
+        raise PssError(f"{what}: {msg}" + (f" [{detail}]" if detail else ""))

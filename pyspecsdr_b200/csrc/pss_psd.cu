@@ -1,0 +1,530 @@
+// Fused PSD kernel: window -> Stockham FFT (radix-16 passes through shared memory) -> fftshift ->
+// 10*log10(|X|^2 + 1e-10) [-> 5-bin smoothing, median-10 dB clamp, row statistics, W-column resample]
+// in ONE launch, one frame per group of N/16 threads.
+//
+// Replaces compute_fft (signal_processing.py:243-264), the main-loop epilogue
+// (pyspecsdr.py:2278-2283), the header read-outs (pyspecsdr.py:388-389), the np.interp column
+// resample of the draw_* functions (pyspecsdr.py:1378-1382 etc.) and the scanner's per-step
+// spectrum + peak + above-threshold count (pyspecsdr.py:2542-2552, 1050-1057).
+//
+// Precision: the window multiply and every butterfly are fp64 (the reference runs c64*f64 -> c128
+// pocketfft); SURVEY.md §7.2 shows an fp32 transform misses the 1e-4 dB bar by 10-4000x whenever a
+// strong tone is present.  Only the |X|^2 -> dB tail is fp32.
+#include <math.h>
+
+#include "pss_fft.cuh"
+
+enum { EPI_RAW = 0, EPI_SMOOTH = 1, EPI_SCAN = 2 };
+
+struct PsdParams {
+    const float2* iq;
+    const void* window;   // T[N] or nullptr
+    const void* tw;       // cx<T> per-pass base twiddles
+    long long n_frames;
+    float* db;
+    float* cols;
+    int W;
+    float* stats;
+    float* peak;
+    int* count;
+    int use_abs;
+    float thr;
+};
+
+template <int LOG2N, typename T>
+struct PsdCfg {
+    static constexpr int N = 1 << LOG2N;
+    static constexpr int TPF = N / 16;                       // threads per frame
+    static constexpr int THREADS = TPF > 256 ? TPF : 256;
+    static constexpr int FPC = THREADS / TPF;                // frames per CTA
+    static constexpr int MINB = (sizeof(T) * 2 * N * FPC <= 64 * 1024) ? 2 : 1;
+    static constexpr size_t SMEM = (size_t)FPC * N * sizeof(cx<T>);
+    static constexpr int NP = pss_num_passes(LOG2N);
+};
+
+__device__ __forceinline__ unsigned f2key(float f) {
+    unsigned u = __float_as_uint(f);
+    return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+    unsigned u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    return __uint_as_float(u);
+}
+
+// One Stockham pass P >= 1 (shared -> registers -> shared, or -> `out` on the last pass).
+template <int LOG2N, int P, typename T, typename OutF>
+__device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<T>* __restrict__ tw,
+                                              const int t, OutF&& out) {
+    constexpr int N = 1 << LOG2N, TPF = N / 16;
+    constexpr int BITS = pss_pass_bits(LOG2N, P), R = 1 << BITS, NS = 1 << (4 * P);
+    constexpr int TI = N / R, ITEMS = 16 / R, NP = pss_num_passes(LOG2N);
+    constexpr int TWOFF = (NS - 16) / 15;
+    cx<T> v[16];
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it)
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[it * R + r] = buf[fft_swz(t + it * TPF + r * TI)];
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int j = t + it * TPF;
+        const int k = j & (NS - 1);
+        const cx<T> w = tw[TWOFF + k];
+        twiddle_apply<R, T>(v + it * R, w);
+        fft_regs<R, T>::run(v + it * R);
+        const int base = ((j - k) << BITS) + k;
+#pragma unroll
+        for (int p = 0; p < R; ++p) {
+            const int idx = base + fft_perm<R>(p) * NS;
+            if constexpr (P == NP - 1)
+                out(idx, v[it * R + p]);
+            else
+                buf[fft_swz(idx)] = v[it * R + p];
+        }
+    }
+    if constexpr (P != NP - 1) __syncthreads();
+}
+
+template <int LOG2N, typename T, int EPI>
+__global__ void __launch_bounds__(PsdCfg<LOG2N, T>::THREADS, PsdCfg<LOG2N, T>::MINB)
+psd_kernel(const PsdParams p) {
+    using C = PsdCfg<LOG2N, T>;
+    constexpr int N = C::N, TPF = C::TPF, NP = C::NP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int f = tid / TPF, t = tid % TPF;
+    const long long frame = (long long)blockIdx.x * C::FPC + f;
+    const bool live = frame < p.n_frames;
+    cx<T>* buf = reinterpret_cast<cx<T>*>(smem_raw) + (size_t)f * N;
+    const cx<T>* tw = reinterpret_cast<const cx<T>*>(p.tw);
+
+    // frame-local scratch that aliases the exchange buffer once the last pass has read it
+    float* row = reinterpret_cast<float*>(buf);           // [N] dB, fft-shifted
+    float* srow = row + N;                                // [N] smoothed / clamped
+    unsigned* hist = reinterpret_cast<unsigned*>(srow + N);   // [2][256]
+    double* dscr = reinterpret_cast<double*>(hist + 512);     // [16] per-warp sums
+    float* fscr = reinterpret_cast<float*>(dscr + 16);        // [32] per-warp max / min
+    unsigned* uscr = reinterpret_cast<unsigned*>(fscr + 32);  // [16] select state
+    static_assert(EPI == EPI_RAW || N >= 512, "epilogues need N >= 512");
+
+    // ---- pass 0: global (coalesced 8-byte loads) * window -> radix-16 -> shared
+    {
+        cx<T> v[16];
+        const float2* src = p.iq + frame * N;
+        const T* win = reinterpret_cast<const T*>(p.window);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            const int idx = t + r * TPF;
+            const float2 s = live ? __ldg(src + idx) : make_float2(0.f, 0.f);
+            if (win) {
+                const T w = __ldg(win + idx);
+                v[r] = {(T)s.x * w, (T)s.y * w};
+            } else {
+                v[r] = {(T)s.x, (T)s.y};
+            }
+        }
+        fft_regs<16, T>::run(v);
+        const int base = t << 4;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) buf[fft_swz(base + fft_perm<16>(q))] = v[q];
+    }
+    __syncthreads();
+
+    // ---- |X|^2 -> dB at the fft-shifted position
+    auto emit = [&](int k, const cx<T> X) {
+        const double pw = (double)X.x * (double)X.x + ((double)X.y * (double)X.y + 1e-10);
+        const float d = db_from_power(pw);
+        const int pos = k ^ (N >> 1);
+        if constexpr (EPI == EPI_RAW) {
+            if (live) p.db[frame * N + pos] = d;
+        } else {
+            row[pos] = d;
+        }
+    };
+    if constexpr (NP == 2) {
+        stockham_pass<LOG2N, 1, T>(buf, tw, t, emit);
+    } else if constexpr (NP == 3) {
+        stockham_pass<LOG2N, 1, T>(buf, tw, t, [](int, cx<T>) {});
+        stockham_pass<LOG2N, 2, T>(buf, tw, t, emit);
+    } else {
+        stockham_pass<LOG2N, 1, T>(buf, tw, t, [](int, cx<T>) {});
+        stockham_pass<LOG2N, 2, T>(buf, tw, t, [](int, cx<T>) {});
+        stockham_pass<LOG2N, 3, T>(buf, tw, t, emit);
+    }
+
+    if constexpr (EPI == EPI_SCAN) {
+        // scanner: peak and number of bins above (peak - rel) or above an absolute threshold
+        const int wf = t >> 5, lane = t & 31, nw = TPF / 32;
+        __syncthreads();
+        float vals[16];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            vals[m] = row[t + m * TPF];
+            mx = fmaxf(mx, vals[m]);
+            if (live && p.db) p.db[frame * N + t + m * TPF] = vals[m];
+        }
+        mx = warp_max(mx);
+        if (lane == 0) fscr[wf] = mx;
+        __syncthreads();
+        float peak = fscr[0];
+        for (int w = 1; w < nw; ++w) peak = fmaxf(peak, fscr[w]);
+        const float thr = p.use_abs ? p.thr : peak - p.thr;
+        int cnt = 0;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) cnt += vals[m] > thr;
+        cnt = warp_sum(cnt);
+        if (lane == 0) uscr[wf] = (unsigned)cnt;
+        __syncthreads();
+        if (t == 0 && live) {
+            unsigned tot = 0;
+            for (int w = 0; w < nw; ++w) tot += uscr[w];
+            p.peak[frame] = peak;
+            p.count[frame] = (int)tot;
+        }
+    }
+
+    if constexpr (EPI == EPI_SMOOTH) {
+        constexpr int n = N - 4;
+        const int wf = t >> 5, lane = t & 31, nw = TPF / 32;
+        __syncthreads();                       // row complete
+        // 5-bin 'valid' moving average, 16 consecutive outputs per thread
+        float s[16];
+        unsigned key[16];
+        const int i0 = t * 16;
+        {
+            float d[20];
+            const float4* r4 = reinterpret_cast<const float4*>(row + i0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 x = r4[q];
+                d[4 * q] = x.x; d[4 * q + 1] = x.y; d[4 * q + 2] = x.z; d[4 * q + 3] = x.w;
+            }
+            if (i0 + 16 < N) {
+                const float4 x = r4[4];
+                d[16] = x.x; d[17] = x.y; d[18] = x.z; d[19] = x.w;
+            } else {
+                d[16] = d[17] = d[18] = d[19] = 0.f;
+            }
+#pragma unroll
+            for (int m = 0; m < 16; ++m)
+                s[m] = ((d[m] + d[m + 1]) + (d[m + 2] + d[m + 3]) + d[m + 4]) * 0.2f;
+        }
+        const int nvalid = min(16, n - i0);     // 16, or 12 for the last thread of the frame
+        unsigned kmin = 0xffffffffu, kmax = 0u;
+        bool has_nan = false;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            key[m] = f2key(s[m]);
+            if (m < nvalid) {
+                kmin = min(kmin, key[m]);
+                kmax = max(kmax, key[m]);
+                has_nan |= (s[m] != s[m]);
+            }
+        }
+        if (t < 16) uscr[t] = (t == 0 || t == 5) ? 0xffffffffu : 0u;   // [0]=min [1]=max [4]=cnt_le [5]=min_gt [6]=nan
+        for (int b = t; b < 512; b += TPF) hist[b] = 0u;
+        __syncthreads();
+        kmin = __reduce_min_sync(0xffffffffu, kmin);
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        if (lane == 0) {
+            atomicMin(&uscr[0], kmin);
+            atomicMax(&uscr[1], kmax);
+        }
+        if (__any_sync(0xffffffffu, has_nan) && lane == 0) atomicOr(&uscr[6], 1u);
+        __syncthreads();
+        kmin = uscr[0];
+        kmax = uscr[1];
+        const int common = min(__clz((int)(kmin ^ kmax)), 31);
+        // normalised keys: order preserved, leading bits spread over the occupied range
+#pragma unroll
+        for (int m = 0; m < 16; ++m) key[m] = (key[m] - kmin) << common;
+        // radix select of rank (n-1)/2, four 8-bit digits
+        unsigned rank = (unsigned)((n - 1) / 2), prefix = 0u;
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+            const int shift = 24 - 8 * ps;
+            unsigned* h = hist + (ps & 1) * 256;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const bool match = ps == 0 ? true : (key[m] >> (shift + 8)) == prefix;
+                if (m < nvalid && match) atomicAdd(&h[(key[m] >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (wf == 0) {
+                const uint4 a = reinterpret_cast<const uint4*>(h)[2 * lane];
+                const uint4 b = reinterpret_cast<const uint4*>(h)[2 * lane + 1];
+                const unsigned c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+                unsigned sum = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) sum += c[q];
+                unsigned incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const unsigned hit = __ballot_sync(0xffffffffu, incl > rank);
+                const int L = __ffs(hit) - 1;
+                if (lane == L) {
+                    unsigned r = rank - (incl - sum);
+                    int dg = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (!found) {
+                            if (r < c[q]) { dg = q; found = true; }
+                            else r -= c[q];
+                        }
+                    }
+                    uscr[2] = (unsigned)(8 * lane + dg);
+                    uscr[3] = r;
+                }
+            } else {
+                unsigned* hn = hist + ((ps + 1) & 1) * 256;      // clear the other histogram
+                for (int b = t - 32; b < 256; b += TPF - 32) hn[b] = 0u;
+            }
+            if (TPF == 32) {                                     // single-warp frame: clear here
+                unsigned* hn = hist + ((ps + 1) & 1) * 256;
+                __syncwarp();
+                for (int b = t; b < 256; b += 32) hn[b] = 0u;
+            }
+            __syncthreads();
+            prefix = (prefix << 8) | uscr[2];
+            rank = uscr[3];
+        }
+        const unsigned key1n = prefix;                          // normalised key of the lower median
+        unsigned cnt_le = 0, min_gt = 0xffffffffu;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            if (m < nvalid) {
+                cnt_le += key[m] <= key1n;
+                if (key[m] > key1n) min_gt = min(min_gt, key[m]);
+            }
+        }
+        cnt_le = __reduce_add_sync(0xffffffffu, cnt_le);
+        min_gt = __reduce_min_sync(0xffffffffu, min_gt);
+        if (lane == 0) {
+            atomicAdd(&uscr[4], cnt_le);
+            atomicMin(&uscr[5], min_gt);
+        }
+        __syncthreads();
+        float thr;
+        {
+            const unsigned key2n = ((n & 1) || uscr[4] > (unsigned)(n / 2)) ? key1n : uscr[5];
+            const float v1 = key2f((key1n >> common) + kmin);
+            const float v2 = key2f((key2n >> common) + kmin);
+            thr = (float)(0.5 * ((double)v1 + (double)v2) - 10.0);
+            if (uscr[6]) thr = __int_as_float(0x7fc00000);       // np.median propagates NaN
+        }
+        // clamp, row statistics, store
+        float mx = -INFINITY, mn = INFINITY, fsum = 0.f;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            if (s[m] < thr) s[m] = thr;
+            if (m < nvalid) {
+                mx = fmaxf(mx, s[m]);
+                mn = fminf(mn, s[m]);
+                fsum += s[m];
+            }
+        }
+        {
+            float4* o4 = reinterpret_cast<float4*>(srow + i0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o4[q] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+        }
+        if (live && p.db) {
+            float* dst = p.db + frame * n + i0;
+            if (nvalid == 16) {
+                float4* o4 = reinterpret_cast<float4*>(dst);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) o4[q] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+            } else {
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    if (m < nvalid) dst[m] = s[m];
+            }
+        }
+        mx = warp_max(mx);
+        mn = warp_min(mn);
+        const double dsum = warp_sum((double)fsum);
+        if (lane == 0) {
+            fscr[wf] = mx;
+            fscr[16 + wf] = mn;
+            dscr[wf] = dsum;
+        }
+        __syncthreads();
+        if (live && p.stats && t == 0) {
+            float a = fscr[0], b = fscr[16];
+            double sm = dscr[0];
+            for (int w = 1; w < nw; ++w) {
+                a = fmaxf(a, fscr[w]);
+                b = fminf(b, fscr[16 + w]);
+                sm += dscr[w];
+            }
+            const float nanv = __int_as_float(0x7fc00000);
+            float4 st;
+            st.x = uscr[6] ? nanv : a;                    // np.max
+            st.y = uscr[6] ? nanv : (float)(sm / n);      // np.mean
+            st.z = b;                                     // finite min
+            st.w = a;                                     // finite max
+            reinterpret_cast<float4*>(p.stats)[frame] = st;
+        }
+        if (live && p.cols) {
+            const int W = p.W;
+            const double step = W > 1 ? (double)(n - 1) / (double)(W - 1) : 0.0;
+            for (int c = t; c < W; c += TPF) {
+                const double x = (c == W - 1 && W > 1) ? (double)(n - 1) : c * step;
+                const int j = (int)x;
+                float o;
+                if (j >= n - 1) {
+                    o = srow[n - 1];
+                } else {
+                    const double y0 = srow[j], y1 = srow[j + 1];
+                    o = (float)((y1 - y0) * (x - (double)j) + y0);
+                }
+                p.cols[frame * W + c] = o;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------- host side
+template <typename T>
+static int build_tables(pss_ctx* ctx, int log2n, pss_fft_tables& tab) {
+    const int N = 1 << log2n;
+    const int np = pss_num_passes(log2n);
+    std::vector<cx<T>> tw;
+    for (int ps = 1; ps < np; ++ps) {
+        const long ns = 1L << (4 * ps);
+        const long r = 1L << pss_pass_bits(log2n, ps);
+        for (long k = 0; k < ns; ++k) {
+            const long double a = -2.0L * 3.14159265358979323846264338327950288L * (long double)k /
+                                  (long double)(ns * r);
+            tw.push_back({(T)cosl(a), (T)sinl(a)});
+        }
+    }
+    if (tw.empty()) tw.push_back({(T)1, (T)0});
+    PSS_CUDA(ctx, cudaMalloc(&tab.twiddle, tw.size() * sizeof(cx<T>)));
+    PSS_CUDA(ctx, cudaMemcpy(tab.twiddle, tw.data(), tw.size() * sizeof(cx<T>), cudaMemcpyHostToDevice));
+    std::vector<T> w(N);
+    for (int kind = PSS_WINDOW_HAMMING; kind <= PSS_WINDOW_HANN; ++kind) {
+        // np.hamming / np.hanning: a - b*cos(2*pi*n/(N-1)), symmetric (signal_processing.py:246)
+        const long double a = kind == PSS_WINDOW_HAMMING ? 0.54L : 0.5L;
+        const long double b = kind == PSS_WINDOW_HAMMING ? 0.46L : 0.5L;
+        for (int i = 0; i < N; ++i)
+            w[i] = (T)(a - b * cosl(2.0L * 3.14159265358979323846264338327950288L * (long double)i /
+                                    (long double)(N - 1)));
+        PSS_CUDA(ctx, cudaMalloc(&tab.window[kind], N * sizeof(T)));
+        PSS_CUDA(ctx, cudaMemcpy(tab.window[kind], w.data(), N * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    return PSS_OK;
+}
+
+template <int LOG2N, typename T, int EPI>
+static int launch_one(pss_ctx* ctx, const PsdParams& p) {
+    using C = PsdCfg<LOG2N, T>;
+    auto kern = psd_kernel<LOG2N, T, EPI>;
+    static bool configured[16] = {};
+    if (!configured[ctx->device & 15]) {
+        PSS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+        configured[ctx->device & 15] = true;
+    }
+    const long long grid = (p.n_frames + C::FPC - 1) / C::FPC;
+    kern<<<(unsigned)grid, C::THREADS, C::SMEM, ctx->stream>>>(p);
+    PSS_LAUNCH_CHECK(ctx);
+    return PSS_OK;
+}
+
+template <typename T, int EPI>
+static int launch_by_n(pss_ctx* ctx, int log2n, const PsdParams& p) {
+    switch (log2n) {
+        case 9: return launch_one<9, T, EPI>(ctx, p);
+        case 10: return launch_one<10, T, EPI>(ctx, p);
+        case 11: return launch_one<11, T, EPI>(ctx, p);
+        case 12: return launch_one<12, T, EPI>(ctx, p);
+        case 13: return launch_one<13, T, EPI>(ctx, p);
+        default: break;
+    }
+    if constexpr (EPI == EPI_RAW) {
+        switch (log2n) {
+            case 6: return launch_one<6, T, EPI>(ctx, p);
+            case 7: return launch_one<7, T, EPI>(ctx, p);
+            case 8: return launch_one<8, T, EPI>(ctx, p);
+            default: break;
+        }
+    }
+    return PSS_ERR_UNSUPPORTED;
+}
+
+static int ilog2_exact(int n) {
+    if (n <= 0 || (n & (n - 1))) return -1;
+    int l = 0;
+    while ((1 << l) < n) ++l;
+    return l;
+}
+
+static int get_tables(pss_ctx* ctx, int log2n, pss_fft_tables** out) {
+    auto it = ctx->fft_tables.find(log2n);
+    if (it == ctx->fft_tables.end()) {
+        pss_fft_tables tab;
+        int rc = build_tables<double>(ctx, log2n, tab);
+        if (rc != PSS_OK) return rc;
+        it = ctx->fft_tables.emplace(log2n, tab).first;
+    }
+    *out = &it->second;
+    return PSS_OK;
+}
+
+// Device-pointer PSD; see pss.h.
+extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, int window,
+                               int epilogue, int precision, const pss_psd_out* out) {
+    if (!ctx || !iq || !out || n_frames < 0) return PSS_ERR_ARG;
+    if (window < 0 || window > 2 || (epilogue != PSS_EPI_RAW && epilogue != PSS_EPI_SMOOTH_CLAMP))
+        return PSS_ERR_ARG;
+    if (precision != PSS_PREC_FP64) return PSS_ERR_UNSUPPORTED;
+    if (epilogue == PSS_EPI_RAW && !out->db) return PSS_ERR_ARG;
+    if (epilogue == PSS_EPI_RAW && (out->cols || out->stats)) return PSS_ERR_UNSUPPORTED;
+    if (out->cols && out->W < 1) return PSS_ERR_ARG;
+    const int log2n = ilog2_exact(N);
+    if (log2n < 0) return PSS_ERR_UNSUPPORTED;
+    if (n_frames == 0) return PSS_OK;
+    if (n_frames > 0x7fffffffLL) return PSS_ERR_ARG;
+    pss_fft_tables* tab;
+    int rc = get_tables(ctx, log2n, &tab);
+    if (rc != PSS_OK) return rc;
+    PsdParams p{};
+    p.iq = reinterpret_cast<const float2*>(iq);
+    p.window = window == PSS_WINDOW_NONE ? nullptr : tab->window[window];
+    p.tw = tab->twiddle;
+    p.n_frames = n_frames;
+    p.db = out->db;
+    p.cols = out->cols;
+    p.W = out->W;
+    p.stats = out->stats;
+    if (epilogue == PSS_EPI_RAW) return launch_by_n<double, EPI_RAW>(ctx, log2n, p);
+    return launch_by_n<double, EPI_SMOOTH>(ctx, log2n, p);
+}
+
+extern "C" int pss_scan_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_steps, int use_abs,
+                                float thr_db, float* peak_db, int32_t* count_above, float* db_rows) {
+    if (!ctx || !iq || !peak_db || !count_above || n_steps < 0) return PSS_ERR_ARG;
+    const int log2n = ilog2_exact(N);
+    if (log2n < 0) return PSS_ERR_UNSUPPORTED;
+    if (n_steps == 0) return PSS_OK;
+    if (n_steps > 0x7fffffffLL) return PSS_ERR_ARG;
+    pss_fft_tables* tab;
+    int rc = get_tables(ctx, log2n, &tab);
+    if (rc != PSS_OK) return rc;
+    PsdParams p{};
+    p.iq = reinterpret_cast<const float2*>(iq);
+    p.window = nullptr;
+    p.tw = tab->twiddle;
+    p.n_frames = n_steps;
+    p.db = db_rows;
+    p.peak = peak_db;
+    p.count = count_above;
+    p.use_abs = use_abs;
+    p.thr = thr_db;
+    return launch_by_n<double, EPI_SCAN>(ctx, log2n, p);
+}

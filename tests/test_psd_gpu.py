@@ -1,0 +1,117 @@
+"""GPU parity: fused PSD kernel (through the C ABI) vs the CPU oracle.  Tolerance: 1e-4 dB per bin
+(BASELINE.json north_star), applied to every bin of every frame."""
+import numpy as np
+import pytest
+
+from oracle import ref_dsp as O
+from pyspecsdr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+TOL_DB = 1e-4
+
+
+def frames(kind, n, count, seed0=0):
+    return np.stack([synth.make(kind, n, seed=seed0 + s) for s in range(count)])
+
+
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("kind", ["noise", "tone40", "tone60", "wbfm"])
+def test_psd_raw_vs_oracle(ctx, n, kind):
+    x = frames(kind, n, 5 if n <= 4096 else 3, seed0=n % 13)
+    got = ctx.psd(x, window="hamming")["db"]
+    want = O.psd_db(x)
+    assert got.shape == want.shape and got.dtype == np.float32
+    err = np.max(np.abs(got.astype(np.float64) - want))
+    assert err <= TOL_DB, f"max |dB| error {err:.3e}"
+
+
+@pytest.mark.parametrize("window", ["none", "hann"])
+def test_psd_other_windows(ctx, window):
+    x = frames("tone60", 4096, 3)
+    got = ctx.psd(x, window=window)["db"]
+    assert np.max(np.abs(got - O.psd_db(x, window=window))) <= TOL_DB
+
+
+def test_psd_golden(ctx, golden):
+    g = golden("psd")
+    for kind, n in (("noise", 1024), ("tone40", 4096), ("tone60", 8192), ("wbfm", 4096)):
+        x = synth.make(kind, n, seed=n % 97)
+        got = ctx.psd(x)["db"][0]
+        assert np.max(np.abs(got - g[f"{kind}_{n}"])) <= TOL_DB
+    got = ctx.psd(synth.impulse(1024, 3))["db"][0]
+    assert np.max(np.abs(got - g["impulse_1024"])) <= TOL_DB
+    got = ctx.psd(np.zeros(1024, np.complex64))["db"][0]
+    np.testing.assert_allclose(got, -100.0, atol=TOL_DB)
+
+
+def test_psd_ragged_batch_and_empty(ctx):
+    # frame counts that do not fill the last CTA (4 frames of 1024 per CTA), and an empty batch
+    for count in (1, 3, 7):
+        x = frames("tone40", 1024, count)
+        assert np.max(np.abs(ctx.psd(x)["db"] - O.psd_db(x))) <= TOL_DB
+    assert ctx.psd(np.zeros((0, 1024), np.complex64))["db"].shape == (0, 1024)
+
+
+@pytest.mark.parametrize("n", [512, 1024, 4096, 8192])
+@pytest.mark.parametrize("kind", ["noise", "tone40", "wbfm"])
+def test_psd_epilogue_vs_oracle(ctx, n, kind):
+    x = frames(kind, n, 4, seed0=3)
+    W = 193
+    res = ctx.psd(x, epilogue=True, W=W, want_stats=True)
+    for f in range(len(x)):
+        want = O.psd_epilogue(O.psd_db(x[f]))
+        assert res["db"][f].shape == (n - 4,)
+        assert np.max(np.abs(res["db"][f] - want)) <= TOL_DB
+        assert np.max(np.abs(res["cols"][f] - O.resample_cols(want, W))) <= TOL_DB
+        pk, av = O.peak_avg(want)
+        st = res["stats"][f]
+        assert abs(st[0] - pk) <= TOL_DB and abs(st[1] - av) <= TOL_DB
+        assert abs(st[2] - want.min()) <= TOL_DB and abs(st[3] - want.max()) <= TOL_DB
+
+
+def test_psd_epilogue_golden(ctx, golden):
+    g = golden("epilogue")
+    for kind, n in (("noise", 1024), ("tone40", 4096), ("wbfm", 4096), ("tone60", 8192)):
+        x = synth.make(kind, n, seed=5)
+        got = ctx.psd(x, epilogue=True)["db"][0]
+        assert np.max(np.abs(got - g[f"{kind}_{n}"])) <= TOL_DB
+
+
+def test_psd_epilogue_constant_row(ctx):
+    # all-zero input: every bin is exactly -100 dB, the median select sees all-equal keys
+    res = ctx.psd(np.zeros((2, 1024), np.complex64), epilogue=True, want_stats=True)
+    np.testing.assert_allclose(res["db"], -100.0, atol=TOL_DB)
+    np.testing.assert_allclose(res["stats"], -100.0, atol=TOL_DB)
+
+
+def test_psd_linearity_property(ctx):
+    # size-independent property at a bench-sized frame: scaling the input by 2 adds 20*log10(2) dB
+    x = frames("tone40", 4096, 2)
+    a = ctx.psd(x, window="hamming")["db"]
+    b = ctx.psd((2 * x).astype(np.complex64), window="hamming")["db"]
+    strong = a > -60          # away from the +1e-10 floor
+    assert np.max(np.abs((b - a)[strong] - 20 * np.log10(2.0))) <= 2e-4
+
+
+def test_scanner_vs_oracle_and_golden(ctx, golden):
+    g = golden("scanner")
+    fr = synth.scanner_frames(24, 2048, seed=3)
+    peak, count, rows = ctx.scan(fr, rel_db=20.0, want_rows=True)
+    assert np.max(np.abs(peak - g["peak"])) <= TOL_DB
+    assert np.max(np.abs(rows - O.psd_db(fr, window="none"))) <= TOL_DB
+    # integer result: exact unless a bin sits within the dB tolerance of the threshold
+    for k in range(len(fr)):
+        db = O.psd_db(fr[k], window="none")
+        lo = int(np.sum(db > db.max() - 20 + 2 * TOL_DB))
+        hi = int(np.sum(db > db.max() - 20 - 2 * TOL_DB))
+        assert lo <= count[k] <= hi
+    assert np.mean(count == g["count"]) >= 0.9
+    fr8 = synth.scanner_frames(6, 8192, seed=4)
+    peak, count = ctx.scan(fr8)
+    assert np.max(np.abs(peak - g["peak8k"])) <= TOL_DB
+    assert np.max(np.abs(count - g["count8k"])) <= 1
+    # absolute-threshold variant (scan_frequencies, pyspecsdr.py:1055-1057)
+    peak, count = ctx.scan(fr, threshold=-40.0)
+    for k in range(len(fr)):
+        db = O.psd_db(fr[k], window="none")
+        assert int(np.sum(db > -40 + 2 * TOL_DB)) <= count[k] <= int(np.sum(db > -40 - 2 * TOL_DB))
