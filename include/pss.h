@@ -52,9 +52,10 @@ void        pss_destroy(pss_ctx* ctx);
 const char* pss_strerror(int status);
 const char* pss_last_error(const pss_ctx* ctx);      /* text of the last CUDA failure */
 int         pss_version(void);
-/* Adopt a caller-owned cudaStream_t (e.g. torch's current stream) for all *_dev calls; NULL
- * restores the context's own stream. */
+/* Adopt a caller-owned cudaStream_t (e.g. torch's current stream) for all *_dev calls; NULL is
+ * the CUDA default stream.  pss_use_own_stream() goes back to the context's private stream. */
 int         pss_set_stream(pss_ctx* ctx, void* cuda_stream);
+int         pss_use_own_stream(pss_ctx* ctx);
 int         pss_sync(pss_ctx* ctx);
 /* Number of kernels this library has launched on this context (bench.py's gpu_launches). */
 int64_t     pss_kernel_launches(const pss_ctx* ctx);

@@ -29,6 +29,7 @@ def _signatures():
         "pss_last_error": (C.c_char_p, [vp]),
         "pss_version": (i32, []),
         "pss_set_stream": (i32, [vp, vp]),
+        "pss_use_own_stream": (i32, [vp]),
         "pss_sync": (i32, [vp]),
         "pss_kernel_launches": (i64, [vp]),
         "pss_host_alloc": (vp, [C.c_size_t]),

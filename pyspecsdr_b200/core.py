@@ -56,8 +56,12 @@ class Context:
         _lib.check(self._h, rc, what)
 
     def set_stream(self, cuda_stream_handle):
-        """Adopt a cudaStream_t (int), e.g. torch.cuda.current_stream().cuda_stream; None = own."""
-        self._ck(lib.pss_set_stream(self._h, cuda_stream_handle or None), "pss_set_stream")
+        """Adopt a cudaStream_t (int), e.g. torch.cuda.current_stream().cuda_stream (0 = the CUDA
+        default stream); None goes back to the context's own stream."""
+        if cuda_stream_handle is None:
+            self._ck(lib.pss_use_own_stream(self._h), "pss_use_own_stream")
+        else:
+            self._ck(lib.pss_set_stream(self._h, cuda_stream_handle or None), "pss_set_stream")
 
     def sync(self):
         self._ck(lib.pss_sync(self._h), "pss_sync")

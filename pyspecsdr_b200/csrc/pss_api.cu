@@ -95,7 +95,13 @@ const char* pss_last_error(const pss_ctx* ctx) { return ctx ? ctx->last_error.c_
 
 int pss_set_stream(pss_ctx* ctx, void* cuda_stream) {
     if (!ctx) return PSS_ERR_ARG;
-    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    return PSS_OK;
+}
+
+int pss_use_own_stream(pss_ctx* ctx) {
+    if (!ctx) return PSS_ERR_ARG;
+    ctx->stream = ctx->own_stream;
     return PSS_OK;
 }
 
