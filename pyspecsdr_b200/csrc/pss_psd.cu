@@ -53,12 +53,11 @@ __device__ __forceinline__ float key2f(unsigned k) {
 
 // One Stockham pass P >= 1 (shared -> registers -> shared, or -> `out` on the last pass).
 template <int LOG2N, int P, typename T, typename OutF>
-__device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<T>* __restrict__ tw,
+__device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<T>* __restrict__ wpre,
                                               const int t, OutF&& out) {
     constexpr int N = 1 << LOG2N, TPF = N / 16;
     constexpr int BITS = pss_pass_bits(LOG2N, P), R = 1 << BITS, NS = 1 << (4 * P);
     constexpr int TI = N / R, ITEMS = 16 / R, NP = pss_num_passes(LOG2N);
-    constexpr int TWOFF = (NS - 16) / 15;
     cx<T> v[16];
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it)
@@ -69,8 +68,7 @@ __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<
     for (int it = 0; it < ITEMS; ++it) {
         const int j = t + it * TPF;
         const int k = j & (NS - 1);
-        const cx<T> w = tw[TWOFF + k];
-        twiddle_apply<R, T>(v + it * R, w);
+        twiddle_apply<R, T>(v + it * R, wpre[it]);
         fft_regs<R, T>::run(v + it * R);
         const int base = ((j - k) << BITS) + k;
 #pragma unroll
@@ -97,6 +95,16 @@ psd_kernel(const PsdParams p) {
     const bool live = frame < p.n_frames;
     cx<T>* buf = reinterpret_cast<cx<T>*>(smem_raw) + (size_t)f * N;
     const cx<T>* tw = reinterpret_cast<const cx<T>*>(p.tw);
+    // base twiddles of every pass depend only on the thread: fetch them before anything else so the
+    // loads are never exposed behind a barrier
+    cx<T> wpre[3][8];
+#pragma unroll
+    for (int ps = 1; ps < NP; ++ps) {
+        const int bits = pss_pass_bits(LOG2N, ps), ns = 1 << (4 * ps), items = 16 >> bits;
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+            if (it < items) wpre[ps - 1][it] = tw[(ns - 16) / 15 + ((t + it * TPF) & (ns - 1))];
+    }
 
     // frame-local scratch that aliases the exchange buffer once the last pass has read it
     float* row = reinterpret_cast<float*>(buf);           // [N] dB, fft-shifted
@@ -142,14 +150,14 @@ psd_kernel(const PsdParams p) {
         }
     };
     if constexpr (NP == 2) {
-        stockham_pass<LOG2N, 1, T>(buf, tw, t, emit);
+        stockham_pass<LOG2N, 1, T>(buf, wpre[0], t, emit);
     } else if constexpr (NP == 3) {
-        stockham_pass<LOG2N, 1, T>(buf, tw, t, [](int, cx<T>) {});
-        stockham_pass<LOG2N, 2, T>(buf, tw, t, emit);
+        stockham_pass<LOG2N, 1, T>(buf, wpre[0], t, [](int, cx<T>) {});
+        stockham_pass<LOG2N, 2, T>(buf, wpre[1], t, emit);
     } else {
-        stockham_pass<LOG2N, 1, T>(buf, tw, t, [](int, cx<T>) {});
-        stockham_pass<LOG2N, 2, T>(buf, tw, t, [](int, cx<T>) {});
-        stockham_pass<LOG2N, 3, T>(buf, tw, t, emit);
+        stockham_pass<LOG2N, 1, T>(buf, wpre[0], t, [](int, cx<T>) {});
+        stockham_pass<LOG2N, 2, T>(buf, wpre[1], t, [](int, cx<T>) {});
+        stockham_pass<LOG2N, 3, T>(buf, wpre[2], t, emit);
     }
 
     if constexpr (EPI == EPI_SCAN) {
