@@ -98,6 +98,69 @@ int pss_scan_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_steps, int use_
 int pss_scan_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_steps, int use_abs,
                      float thr_db, float* peak_db, int32_t* count_above, float* db_rows);
 
+/* ------------------------------------------------------------------ demodulation
+ * Replaces demodulate_signal(samples, sample_rate, mode)  signal_processing.py:220-240 and the
+ * per-mode chains demodulate_nfm :91-116, demodulate_wfm :119-176 (+ iq_correction :46-80),
+ * demodulate_am :179-195, demodulate_ssb :198-217, RAW :237-238.
+ *
+ * Filter DESIGN stays with the caller (the Python shim designs with scipy exactly as the reference
+ * does and hands the coefficients / response tables over once per (mode, sample_rate, block
+ * length)); a plan owns their device copies.  Every block is independent (zero initial filter
+ * state, per-block peak normalisation), exactly like the reference.
+ *
+ * PSS_PLAN_DECIM (NFM, WFM): fp32 discriminator -> [65-tap FIR | Butterworth low-pass + de-emphasis]
+ *   -> scipy.signal.decimate(q) = 8th-order Chebyshev-I sosfiltfilt (odd extension 27, sosfilt_zi
+ *   initial conditions) -> [::q] -> / max|.| * norm.  Evaluated in "chunk-table" form: fp64 tensor
+ *   -core (DMMA) products of the discriminator stream with precomputed response tables, then
+ *   blocked scans of the 8/16-dimensional filter state over the chunk sequence.
+ *   Output: audio[n_frames][n_out][2] float32 (L == R, as in the reference).
+ * PSS_PLAN_FIR (USB, LSB): 65-tap FIR on the I channel (the reference's hilbert() is an identity on
+ *   the real part, USB == LSB) -> / max|.| * 0.95.          Output: audio[n_frames][N] float32 mono.
+ * PSS_PLAN_SOS (AM): |x| - mean -> 5-section Butterworth band-pass (fp64) -> / max|.| * 0.95.
+ *                                                            Output: audio[n_frames][N] float32 mono.
+ * PSS_PLAN_RAW: real(iq_correction(x)).                      Output: audio[n_frames][N] float32.
+ */
+enum { PSS_PLAN_DECIM = 0, PSS_PLAN_FIR = 1, PSS_PLAN_SOS = 2, PSS_PLAN_RAW = 3 };
+
+typedef struct {
+    int kind;              /* PSS_PLAN_* */
+    int mode;              /* PSS_MODE_* */
+    int N;                 /* IQ samples per block */
+    /* --- PSS_PLAN_DECIM (see pyspecsdr_b200/filters.py: build_decim_plan) */
+    int q, n_out, lead, SF, SB, n_body, m_tail, tail_start, tail_len;
+    int scan_block_f, scan_block_b;     /* block lengths of the forward / backward state scans */
+    float scale, norm;
+    const double* body;    /* [(SF+SB+1)][q+lead] response tables of one body chunk */
+    const double* AF;      /* [SF][SF]   forward state transition over one chunk */
+    const double* AFB;     /* [SF][SF]   AF ^ scan_block_f */
+    const double* AB;      /* [SB][SB]   backward state transition */
+    const double* ABB;     /* [SB][SB]   AB ^ scan_block_b */
+    const double* MB;      /* [SB][SF] */
+    const double* CR;      /* [SF] */
+    const double* CB;      /* [SB] */
+    double DB;
+    const double* head;    /* [(SF+1)][28] */
+    const double* tail_T;  /* [(SB+m_tail)][tail_len] */
+    const double* tail_M;  /* [(SB+m_tail)][SF] */
+    /* --- PSS_PLAN_FIR */
+    const double* taps;    /* [n_taps] */
+    int n_taps;
+    /* --- PSS_PLAN_SOS */
+    const double* sos;     /* [n_sections][6] scipy layout b0 b1 b2 a0 a1 a2 */
+    int n_sections;
+} pss_demod_desc;
+
+typedef struct pss_demod_plan pss_demod_plan;
+
+int  pss_demod_plan_create(pss_ctx* ctx, const pss_demod_desc* desc, pss_demod_plan** out);
+void pss_demod_plan_destroy(pss_ctx* ctx, pss_demod_plan* plan);
+/* Samples written per block and channel count of a plan's output. */
+int  pss_demod_plan_out_len(const pss_demod_plan* plan);
+int  pss_demod_plan_channels(const pss_demod_plan* plan);
+int  pss_demod_c64(pss_ctx* ctx, pss_demod_plan* plan, const float* iq, int64_t n_frames, float* audio);
+int  pss_demod_c64_dev(pss_ctx* ctx, pss_demod_plan* plan, const float* iq, int64_t n_frames,
+                       float* audio);
+
 #ifdef __cplusplus
 }
 #endif

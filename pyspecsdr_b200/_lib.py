@@ -20,6 +20,22 @@ class PsdOut(C.Structure):
     _fields_ = [("db", C.c_void_p), ("cols", C.c_void_p), ("W", C.c_int), ("stats", C.c_void_p)]
 
 
+class DemodDesc(C.Structure):
+    """Mirror of pss_demod_desc (include/pss.h)."""
+    _dp = C.POINTER(C.c_double)
+    _fields_ = [
+        ("kind", C.c_int), ("mode", C.c_int), ("N", C.c_int),
+        ("q", C.c_int), ("n_out", C.c_int), ("lead", C.c_int), ("SF", C.c_int), ("SB", C.c_int),
+        ("n_body", C.c_int), ("m_tail", C.c_int), ("tail_start", C.c_int), ("tail_len", C.c_int),
+        ("scan_block_f", C.c_int), ("scan_block_b", C.c_int),
+        ("scale", C.c_float), ("norm", C.c_float),
+        ("body", _dp), ("AF", _dp), ("AFB", _dp), ("AB", _dp), ("ABB", _dp), ("MB", _dp), ("CR", _dp),
+        ("CB", _dp), ("DB", C.c_double), ("head", _dp), ("tail_T", _dp), ("tail_M", _dp),
+        ("taps", _dp), ("n_taps", C.c_int),
+        ("sos", _dp), ("n_sections", C.c_int),
+    ]
+
+
 def _signatures():
     vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
     return {
@@ -38,6 +54,12 @@ def _signatures():
         "pss_psd_c64_dev": (i32, [vp, vp, i32, i64, i32, i32, i32, C.POINTER(PsdOut)]),
         "pss_scan_c64": (i32, [vp, vp, i32, i64, i32, f32, vp, vp, vp]),
         "pss_scan_c64_dev": (i32, [vp, vp, i32, i64, i32, f32, vp, vp, vp]),
+        "pss_demod_plan_create": (i32, [vp, C.POINTER(DemodDesc), C.POINTER(vp)]),
+        "pss_demod_plan_destroy": (None, [vp, vp]),
+        "pss_demod_plan_out_len": (i32, [vp]),
+        "pss_demod_plan_channels": (i32, [vp]),
+        "pss_demod_c64": (i32, [vp, vp, vp, i64, vp]),
+        "pss_demod_c64_dev": (i32, [vp, vp, vp, i64, vp]),
     }
 
 

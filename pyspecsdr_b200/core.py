@@ -8,8 +8,8 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
-from ._lib import PsdOut, PssError, lib
+from . import _lib, filters
+from ._lib import DemodDesc, PsdOut, PssError, lib
 
 WINDOWS = {"none": 0, "hamming": 1, "hann": 2, None: 0}
 
@@ -31,6 +31,63 @@ def _as_frames(samples) -> np.ndarray:
     return x
 
 
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class DemodPlan:
+    """Device-resident filter tables for one (mode, sample_rate, block length)."""
+
+    def __init__(self, ctx: "Context", mode: str, fs: float, N: int):
+        self.ctx, self.mode, self.fs, self.N = ctx, mode, float(fs), int(N)
+        desc = DemodDesc()
+        desc.mode = filters.MODES[mode]
+        desc.N = N
+        keep = []
+
+        def arr(a):
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            keep.append(a)
+            return _dp(a)
+
+        if mode in ("NFM", "WFM"):
+            p = filters.build_decim_plan(mode, fs, N)
+            self.host_plan = p
+            desc.kind = 0
+            for k in ("q", "n_out", "lead", "SF", "SB", "n_body", "m_tail", "tail_start", "tail_len"):
+                setattr(desc, k, int(getattr(p, k)))
+            desc.scan_block_f = max(1, -(-p.n_body // (256 // p.SF)))
+            desc.scan_block_b = max(1, -(-p.n_body // (256 // p.SB)))
+            desc.scale, desc.norm, desc.DB = np.float32(p.scale), p.norm, p.DB
+            desc.body, desc.AF, desc.AB, desc.MB = arr(p.body), arr(p.AF), arr(p.AB), arr(p.MB)
+            desc.AFB = arr(filters.matrix_power_seq(p.AF, desc.scan_block_f))
+            desc.ABB = arr(filters.matrix_power_seq(p.AB, desc.scan_block_b))
+            desc.CR, desc.CB = arr(p.CR), arr(p.CB)
+            desc.head, desc.tail_T, desc.tail_M = arr(p.head), arr(p.tail_T), arr(p.tail_M)
+        elif mode in ("USB", "LSB"):
+            desc.kind = 1
+            taps = filters.ssb_taps(fs)
+            desc.taps, desc.n_taps = arr(taps), len(taps)
+        elif mode == "AM":
+            desc.kind = 2
+            sos = filters.am_sos()
+            desc.sos, desc.n_sections = arr(sos), len(sos)
+        elif mode == "RAW":
+            desc.kind = 3
+        else:
+            raise ValueError(f"no demodulation plan for mode {mode!r}")
+        h = C.c_void_p()
+        ctx._ck(lib.pss_demod_plan_create(ctx._h, C.byref(desc), C.byref(h)), f"pss_demod_plan_create({mode})")
+        self._h = h
+        self.out_len = int(lib.pss_demod_plan_out_len(h))
+        self.channels = int(lib.pss_demod_plan_channels(h))
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            lib.pss_demod_plan_destroy(self.ctx._h, self._h)
+        self._h = None
+
+
 class Context:
     def __init__(self, device: int = 0):
         h = C.c_void_p()
@@ -39,10 +96,14 @@ class Context:
             raise PssError(f"pss_init(device={device}): {lib.pss_strerror(rc).decode()}")
         self._h = h
         self.device = device
+        self._plans = {}
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
         if getattr(self, "_h", None):
+            for p in self._plans.values():
+                p.close()
+            self._plans.clear()
             lib.pss_destroy(self._h)
             self._h = None
 
@@ -116,3 +177,23 @@ class Context:
         use_abs, thr = (0, rel_db) if threshold is None else (1, threshold)
         self._ck(lib.pss_scan_c64_dev(self._h, _ptr(iq), N, n_steps, use_abs, thr, _ptr(peak), _ptr(count),
                                       _ptr(rows)), "pss_scan_c64_dev")
+
+    # ------------------------------------------------------------------ demodulation
+    def demod_plan(self, mode: str, fs: float, N: int) -> DemodPlan:
+        key = (mode, float(fs), int(N))
+        if key not in self._plans:
+            self._plans[key] = DemodPlan(self, mode, fs, N)
+        return self._plans[key]
+
+    def demod(self, samples, fs: float, mode: str) -> np.ndarray:
+        """Batched demodulate_signal for one mode.  Returns float32 [F, out_len, channels]
+        (channels = 2 for NFM/WFM, 1 for AM/USB/LSB/RAW)."""
+        x = _as_frames(samples)
+        F, N = x.shape
+        plan = self.demod_plan(mode, fs, N)
+        out = np.empty((F, plan.out_len, plan.channels), np.float32)
+        self._ck(lib.pss_demod_c64(self._h, plan._h, x.ctypes.data, F, out.ctypes.data), f"pss_demod_c64({mode})")
+        return out
+
+    def demod_dev(self, plan: DemodPlan, iq, n_frames: int, audio):
+        self._ck(lib.pss_demod_c64_dev(self._h, plan._h, _ptr(iq), n_frames, _ptr(audio)), "pss_demod_c64_dev")
