@@ -161,6 +161,49 @@ int  pss_demod_c64(pss_ctx* ctx, pss_demod_plan* plan, const float* iq, int64_t 
 int  pss_demod_c64_dev(pss_ctx* ctx, pss_demod_plan* plan, const float* iq, int64_t n_frames,
                        float* audio);
 
+/* ------------------------------------------------------------------ display accumulate
+ * Replaces the numeric part of draw_waterfall (pyspecsdr.py:1351-1358, 1373-1398),
+ * draw_gradient_waterfall (:1649-1696) and draw_persistence (:1521-1556): a history of the last
+ * `rows_max` dB rows (30 waterfall / 10 persistence), finite min/max over the whole stack, every
+ * row resampled to W columns with np.interp semantics, normalised (v - min) / (max - min).
+ *
+ * The history is not a separate ring: the PSD kernel already leaves every row's W-column resample
+ * (`cols`) and finite min/max (`stats`) in device memory in frame order, so the history of frame t
+ * is simply frames t, t-1, ..., t-rows_max+1 of those arrays.  Render r (0 <= r < n_renders) draws
+ * the display as it stands after frame  t = first + r*step.
+ *   norm   [n_renders][rows_max][W]  newest row first (the order draw_waterfall walks
+ *                                    reversed(WATERFALL_HISTORY)); rows older than frame 0 are NaN
+ *   minmax [n_renders][2]            stack min, max
+ *   guard_zero_range: 0 = waterfall (divide by max-min as is), 1 = gradient / persistence
+ *                     (range 0 is replaced by 1, pyspecsdr.py:1528-1530, 1657-1659)
+ */
+int pss_display_render_dev(pss_ctx* ctx, const float* cols, const float* stats, int W, int64_t n_frames,
+                           int rows_max, int64_t first, int64_t step, int64_t n_renders,
+                           int guard_zero_range, float* norm, float* minmax);
+int pss_display_render(pss_ctx* ctx, const float* cols, const float* stats, int W, int64_t n_frames,
+                       int rows_max, int64_t first, int64_t step, int64_t n_renders,
+                       int guard_zero_range, float* norm, float* minmax);
+
+/* ------------------------------------------------------------------ whole main-loop iteration, batched
+ * One call = what pyspecsdr.py's main loop does per SDR read (pyspecsdr.py:2236-2283 plus the
+ * draw_waterfall accumulate), for a batch of reads ("blocks") that are already in HOST memory:
+ *   audio  = demodulate_signal(block, fs, mode)            -> plan (PSS_PLAN_*)
+ *   rows   = compute_fft(frame) + smoothing + clamp        -> every N_fft-sample frame of the block
+ *   header peak/avg, W-column resample, waterfall history normalisation after each block.
+ * Host pointers in, host pointers out; the copies are inside the call (pinned memory from
+ * pss_host_alloc makes them run at PCIe speed).  Any output pointer may be NULL.
+ *   audio  [n_blocks][out_len][channels]          cols   [n_blocks*fpb][W]     (fpb = N_block / N_fft)
+ *   stats  [n_blocks*fpb][4]                      db     [n_blocks*fpb][N_fft-4]
+ *   norm   [n_blocks][rows_max][W]                minmax [n_blocks][2]
+ */
+typedef struct {
+    int N_block, N_fft, W, rows_max;
+    pss_demod_plan* plan;          /* NULL = no demodulation */
+    float *audio, *cols, *stats, *db, *norm, *minmax;
+} pss_pipeline_io;
+
+int pss_pipeline_c64(pss_ctx* ctx, const float* iq_host, int64_t n_blocks, const pss_pipeline_io* io);
+
 #ifdef __cplusplus
 }
 #endif

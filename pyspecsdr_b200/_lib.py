@@ -36,6 +36,13 @@ class DemodDesc(C.Structure):
     ]
 
 
+class PipelineIO(C.Structure):
+    """Mirror of pss_pipeline_io (include/pss.h)."""
+    _fields_ = [("N_block", C.c_int), ("N_fft", C.c_int), ("W", C.c_int), ("rows_max", C.c_int),
+                ("plan", C.c_void_p), ("audio", C.c_void_p), ("cols", C.c_void_p), ("stats", C.c_void_p),
+                ("db", C.c_void_p), ("norm", C.c_void_p), ("minmax", C.c_void_p)]
+
+
 def _signatures():
     vp, i32, i64, f32, f64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double
     return {
@@ -54,6 +61,9 @@ def _signatures():
         "pss_psd_c64_dev": (i32, [vp, vp, i32, i64, i32, i32, i32, C.POINTER(PsdOut)]),
         "pss_scan_c64": (i32, [vp, vp, i32, i64, i32, f32, vp, vp, vp]),
         "pss_scan_c64_dev": (i32, [vp, vp, i32, i64, i32, f32, vp, vp, vp]),
+        "pss_display_render": (i32, [vp, vp, vp, i32, i64, i32, i64, i64, i64, i32, vp, vp]),
+        "pss_display_render_dev": (i32, [vp, vp, vp, i32, i64, i32, i64, i64, i64, i32, vp, vp]),
+        "pss_pipeline_c64": (i32, [vp, vp, i64, C.POINTER(PipelineIO)]),
         "pss_demod_plan_create": (i32, [vp, C.POINTER(DemodDesc), C.POINTER(vp)]),
         "pss_demod_plan_destroy": (None, [vp, vp]),
         "pss_demod_plan_out_len": (i32, [vp]),

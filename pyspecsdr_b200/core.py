@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib, filters
-from ._lib import DemodDesc, PsdOut, PssError, lib
+from ._lib import DemodDesc, PipelineIO, PsdOut, PssError, lib
 
 WINDOWS = {"none": 0, "hamming": 1, "hann": 2, None: 0}
 
@@ -197,3 +197,67 @@ class Context:
 
     def demod_dev(self, plan: DemodPlan, iq, n_frames: int, audio):
         self._ck(lib.pss_demod_c64_dev(self._h, plan._h, _ptr(iq), n_frames, _ptr(audio)), "pss_demod_c64_dev")
+
+    # ------------------------------------------------------------------ display accumulate
+    def display_render(self, cols, stats, rows_max=30, first=0, step=1, n_renders=None, guard_zero_range=False):
+        """Waterfall / persistence history normalisation from the PSD kernel's `cols` and `stats`.
+        Returns (norm [R, rows_max, W] newest row first, minmax [R, 2])."""
+        cols = np.ascontiguousarray(cols, np.float32)
+        stats = np.ascontiguousarray(stats, np.float32)
+        F, W = cols.shape
+        if n_renders is None:
+            n_renders = (F - 1 - first) // max(step, 1) + 1
+        norm = np.empty((n_renders, rows_max, W), np.float32)
+        mm = np.empty((n_renders, 2), np.float32)
+        self._ck(lib.pss_display_render(self._h, cols.ctypes.data, stats.ctypes.data, W, F, rows_max, first, step,
+                                        n_renders, 1 if guard_zero_range else 0, norm.ctypes.data,
+                                        mm.ctypes.data), "pss_display_render")
+        return norm, mm
+
+    def display_render_dev(self, cols, stats, W, n_frames, norm, minmax, rows_max=30, first=0, step=1,
+                           n_renders=1, guard_zero_range=False):
+        self._ck(lib.pss_display_render_dev(self._h, _ptr(cols), _ptr(stats), W, n_frames, rows_max, first, step,
+                                            n_renders, 1 if guard_zero_range else 0, _ptr(norm), _ptr(minmax)),
+                 "pss_display_render_dev")
+
+    # ------------------------------------------------------------------ batched main-loop iteration
+    def pipeline(self, blocks, fs: float, mode: str = "WFM", n_fft: int = 4096, W: int = 200, rows_max: int = 30,
+                 want_db: bool = False, out=None):
+        """Host buffers in, host buffers out: demodulate_signal + compute_fft/epilogue on every
+        `n_fft` frame + waterfall accumulate after every block, for a batch of blocks.
+        `blocks` is complex64 [n_blocks, N_block] (a pinned buffer makes the copies fast).
+        Returns dict(audio, cols, stats, norm, minmax[, db]).  `out` may supply preallocated arrays."""
+        x = blocks if (isinstance(blocks, np.ndarray) and blocks.dtype == np.complex64 and blocks.ndim == 2
+                       and blocks.flags.c_contiguous) else _as_frames(blocks)
+        nb, N = x.shape
+        fpb = N // n_fft
+        plan = self.demod_plan(mode, fs, N) if mode else None
+        o = out if out is not None else {}
+        def buf(name, shape):
+            if name not in o:
+                o[name] = np.empty(shape, np.float32)
+            return o[name]
+        io = PipelineIO(N, n_fft, W, rows_max, plan._h if plan else None)
+        if plan:
+            io.audio = buf("audio", (nb, plan.out_len, plan.channels)).ctypes.data
+        io.cols = buf("cols", (nb * fpb, W)).ctypes.data
+        io.stats = buf("stats", (nb * fpb, 4)).ctypes.data
+        io.norm = buf("norm", (nb, rows_max, W)).ctypes.data
+        io.minmax = buf("minmax", (nb, 2)).ctypes.data
+        if want_db:
+            io.db = buf("db", (nb * fpb, n_fft - 4)).ctypes.data
+        self._ck(lib.pss_pipeline_c64(self._h, x.ctypes.data, nb, C.byref(io)), "pss_pipeline_c64")
+        return o
+
+    @staticmethod
+    def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+        """numpy array over page-locked memory from pss_host_alloc (freed when the array dies)."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = lib.pss_host_alloc(max(n, 1))
+        if not p:
+            raise PssError("pss_host_alloc failed")
+        raw = (C.c_char * max(n, 1)).from_address(p)
+        arr = np.frombuffer(raw, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        import weakref
+        weakref.finalize(raw, lib.pss_host_free, p)
+        return arr

@@ -87,6 +87,7 @@ void pss_destroy(pss_ctx* ctx) {
     cudaFree(ctx->d_out);
     cudaFree(ctx->d_aux);
     cudaFree(ctx->d_aux2);
+    for (void* b : ctx->p_buf) cudaFree(b);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }

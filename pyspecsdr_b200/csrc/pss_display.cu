@@ -1,2 +1,84 @@
+// Display accumulate: history stack range + normalisation of the W-column rows the PSD kernel
+// emitted (pyspecsdr.py:1351-1358, 1373-1398 waterfall; :1649-1696 gradient; :1521-1556 persistence).
+#include <math.h>
+
 #include "pss_common.cuh"
+
+__global__ void __launch_bounds__(256)
+display_render_kernel(const float* __restrict__ cols, const float* __restrict__ stats, const int W,
+                      const long long n_frames, const int rows_max, const long long first,
+                      const long long step, const int guard, float* __restrict__ norm,
+                      float* __restrict__ minmax) {
+    const long long r = blockIdx.x;
+    const long long t = first + r * step;          // newest frame of this render
+    if (t < 0 || t >= n_frames) return;
+    // stack range over the history rows (each row's finite min/max came with the PSD row)
+    float lo = INFINITY, hi = -INFINITY;
+    for (int y = 0; y < rows_max; ++y) {
+        const long long f = t - y;
+        if (f < 0) break;
+        const float4 st = __ldg(reinterpret_cast<const float4*>(stats) + f);
+        lo = fminf(lo, st.z);
+        hi = fmaxf(hi, st.w);
+    }
+    float range = hi - lo;
+    if (guard && range == 0.f) range = 1.f;
+    if (threadIdx.x == 0) {
+        minmax[2 * r] = lo;
+        minmax[2 * r + 1] = hi;
+    }
+    float* dst = norm + r * (long long)rows_max * W;
+    const int total = rows_max * W;
+    for (int e = threadIdx.x; e < total; e += blockDim.x) {
+        const int y = e / W, c = e - y * W;
+        const long long f = t - y;
+        float v = __int_as_float(0x7fc00000);
+        if (f >= 0) v = (__ldg(cols + f * W + c) - lo) / range;
+        dst[e] = v;
+    }
+}
+
 void pss_display_release(pss_ctx*) {}
+
+extern "C" {
+
+int pss_display_render_dev(pss_ctx* ctx, const float* cols, const float* stats, int W, int64_t n_frames,
+                           int rows_max, int64_t first, int64_t step, int64_t n_renders,
+                           int guard_zero_range, float* norm, float* minmax) {
+    if (!ctx || !cols || !stats || !norm || !minmax || W < 1 || rows_max < 1 || n_frames < 0 || n_renders < 0)
+        return PSS_ERR_ARG;
+    if (n_renders == 0) return PSS_OK;
+    if (first < 0 || step < 0 || first + (n_renders - 1) * step >= n_frames) return PSS_ERR_ARG;
+    if (n_renders > 0x7fffffffLL) return PSS_ERR_ARG;
+    display_render_kernel<<<(unsigned)n_renders, 256, 0, ctx->stream>>>(cols, stats, W, n_frames, rows_max, first,
+                                                                        step, guard_zero_range, norm, minmax);
+    PSS_LAUNCH_CHECK(ctx);
+    return PSS_OK;
+}
+
+int pss_display_render(pss_ctx* ctx, const float* cols, const float* stats, int W, int64_t n_frames,
+                       int rows_max, int64_t first, int64_t step, int64_t n_renders,
+                       int guard_zero_range, float* norm, float* minmax) {
+    if (!ctx || !cols || !stats || !norm || !minmax || W < 1 || rows_max < 1 || n_frames < 0 || n_renders < 0)
+        return PSS_ERR_ARG;
+    if (n_renders == 0) return PSS_OK;
+    PSS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t cols_b = (size_t)n_frames * W * 4, st_b = (size_t)n_frames * 16;
+    const size_t norm_b = (size_t)n_renders * rows_max * W * 4, mm_b = (size_t)n_renders * 8;
+    int rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_in, &ctx->d_in_bytes, cols_b))) return rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_aux, &ctx->d_aux_bytes, st_b))) return rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_out, &ctx->d_out_bytes, norm_b))) return rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_aux2, &ctx->d_aux2_bytes, mm_b))) return rc;
+    PSS_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, cols, cols_b, cudaMemcpyHostToDevice, ctx->stream));
+    PSS_CUDA(ctx, cudaMemcpyAsync(ctx->d_aux, stats, st_b, cudaMemcpyHostToDevice, ctx->stream));
+    rc = pss_display_render_dev(ctx, (const float*)ctx->d_in, (const float*)ctx->d_aux, W, n_frames, rows_max, first,
+                                step, n_renders, guard_zero_range, (float*)ctx->d_out, (float*)ctx->d_aux2);
+    if (rc) return rc;
+    PSS_CUDA(ctx, cudaMemcpyAsync(norm, ctx->d_out, norm_b, cudaMemcpyDeviceToHost, ctx->stream));
+    PSS_CUDA(ctx, cudaMemcpyAsync(minmax, ctx->d_aux2, mm_b, cudaMemcpyDeviceToHost, ctx->stream));
+    PSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PSS_OK;
+}
+
+}  // extern "C"

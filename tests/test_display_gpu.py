@@ -1,0 +1,59 @@
+"""GPU parity: display accumulate (waterfall / gradient / persistence history normalisation) vs the
+oracle, which is itself pinned through what the reference's draw_* functions drew."""
+import numpy as np
+import pytest
+
+from oracle import ref_dsp as O
+from pyspecsdr_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def make_rows(count=34, n=4096):
+    x = np.stack([synth.make("wbfm" if s % 2 else "tone40", n, seed=100 + s) for s in range(count)])
+    ref_rows = [O.psd_epilogue(O.psd_db(r)) for r in x]
+    return x, ref_rows
+
+
+def test_waterfall_history_vs_oracle(ctx):
+    x, ref_rows = make_rows()
+    W = 112
+    res = ctx.psd(x, epilogue=True, W=W, want_stats=True, want_db=False)
+    norm, mm = ctx.display_render(res["cols"], res["stats"], rows_max=30)
+    hist = []
+    mism = 0
+    for s, r in enumerate(ref_rows):
+        want, (lo, hi), colour, level = O.waterfall_accumulate(hist, r, W)
+        got = norm[s, :len(hist)]
+        assert abs(mm[s, 0] - lo) <= 1e-4 and abs(mm[s, 1] - hi) <= 1e-4
+        assert np.max(np.abs(got - want)) <= 1e-5
+        assert np.all(np.isnan(norm[s, len(hist):]))
+        # quantised planes (colour index, glyph level) agree except where norm sits on a boundary
+        mism += np.sum((got * 5).astype(np.int64) != colour)
+        mism += np.sum(((got > 0.25).astype(int) + (got > 0.5) + (got > 0.75)) != level)
+    assert mism <= 1e-4 * 2 * 34 * 30 * W
+
+
+def test_persistence_history_vs_oracle(ctx):
+    x, ref_rows = make_rows(14)
+    W, H = 112, 36
+    res = ctx.psd(x, epilogue=True, W=W, want_stats=True, want_db=False)
+    norm, mm = ctx.display_render(res["cols"], res["stats"], rows_max=10, guard_zero_range=True)
+    hist = []
+    bad = 0
+    for s, r in enumerate(ref_rows):
+        ys, colours, (lo, hi) = O.persistence_accumulate(hist, r, W, H)
+        got = norm[s, :len(hist)][::-1]                      # oldest first, like PERSISTENCE_HISTORY
+        y = ((1 - got.astype(np.float64)) * (H - 1)).astype(np.int64)
+        bad += np.sum(y != ys)
+        assert np.max(np.abs(y - ys)) <= 1
+    assert bad <= 1e-3 * 14 * 10 * W
+
+
+def test_display_strided_renders(ctx):
+    x, ref_rows = make_rows(20, 1024)
+    W = 64
+    res = ctx.psd(x, epilogue=True, W=W, want_stats=True, want_db=False)
+    full, _ = ctx.display_render(res["cols"], res["stats"], rows_max=30)
+    some, _ = ctx.display_render(res["cols"], res["stats"], rows_max=30, first=3, step=8, n_renders=3)
+    np.testing.assert_array_equal(some, full[[3, 11, 19]])
