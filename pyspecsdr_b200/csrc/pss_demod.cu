@@ -17,13 +17,12 @@
 #include "pss_common.cuh"
 
 #define DEMOD_THREADS 256
-#define TILE_CHUNKS 32
 #define EDGE 27
 
 struct DecimDev {
     int mode, N, L, q, n_out, lead, SF, SB, n_body, m_tail, tail_start, tail_len;
     int Bf, Bb;
-    int Kp, KS, NT, rows, stride;
+    int Kp, KS, NT, rows, T, nbuf, tile_floats;
     float scale, norm;
     const double *tabF, *AF, *AFB, *AB, *ABB, *MB, *CR, *CB, *head, *tailT, *tailM;
     double DB;
@@ -58,6 +57,42 @@ __device__ __forceinline__ float2 iq_apply(const float2 s, const IqCorr k) {
     return make_float2(__fmul_rn(i2, k.inv_c), __fmul_rn(q2, k.inv_c));
 }
 
+// atan2f replacement: branch-free, |error| < 1.5e-7 rad (minimax degree-8 polynomial in t^2 for
+// atan(t)/t on [0,1], max fp32 evaluation error 9.3e-8, plus a 2-ulp fast division).  The reference's
+// np.angle is numpy/SVML arctan2 in float32, itself 1-4 ulp; parity is a tolerance (1e-5 RMS on the
+// normalised audio), not bit equality.  Signs follow atan2: result carries the sign of `im`
+// (including -0.0), and is pi-mirrored when `re` is negative; atan2(0, 0) = 0.
+__device__ __forceinline__ float fast_atan2f(const float im, const float re) {
+    const float ax = fabsf(re), ay = fabsf(im);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float t = __fdividef(mn, mx);
+    t = mx == 0.f ? 0.f : t;
+    const float z = t * t;
+    float p = 2.456712816e-03f;
+    p = fmaf(p, z, -1.440130838e-02f);
+    p = fmaf(p, z, 3.978113781e-02f);
+    p = fmaf(p, z, -7.234849502e-02f);
+    p = fmaf(p, z, 1.049894197e-01f);
+    p = fmaf(p, z, -1.416122798e-01f);
+    p = fmaf(p, z, 1.998590658e-01f);
+    p = fmaf(p, z, -3.333259701e-01f);
+    p = fmaf(p, z, 9.999998864e-01f);
+    float r = p * t;
+    r = ay > ax ? 1.57079632679489662f - r : r;
+    r = re < 0.f ? 3.14159265358979324f - r : r;
+    return copysignf(r, im);
+}
+
+// d = angle(a * conj(b)) the way numpy evaluates it on complex64:
+// re = fma(ar, br, ai*bi), im = fma(ai, br, -(ar*bi))  (SIMD fused multiply-add/sub complex product)
+template <bool WFM>
+__device__ __forceinline__ float disc_core(const float2 a, const float2 b, const float scale) {
+    const float re = __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y));
+    const float im = __fmaf_rn(a.y, b.x, -__fmul_rn(a.x, b.y));
+    const float d = fast_atan2f(im, re);
+    return WFM ? d : __fmul_rn(d, scale);
+}
+
 template <bool WFM>
 __device__ __forceinline__ float discriminator(const float2* __restrict__ x, const int g, const int L,
                                                const IqCorr k, const float scale) {
@@ -67,17 +102,83 @@ __device__ __forceinline__ float discriminator(const float2* __restrict__ x, con
         a = iq_apply(a, k);
         b = iq_apply(b, k);
     }
-    // numpy complex64 product a * conj(b): re = fma(ar, br, ai*bi), im = fma(ai, br, -(ar*bi))
-    const float re = __fmaf_rn(a.x, b.x, __fmul_rn(a.y, b.y));
-    const float im = __fmaf_rn(a.y, b.x, -__fmul_rn(a.x, b.y));
-    const float d = atan2f(im, re);
-    return WFM ? d : __fmul_rn(d, scale);
+    return disc_core<WFM>(a, b, scale);
+}
+
+// One contiguous tile of discriminator samples d[g0 .. g0+E) (zero outside [0, L)) is produced in two
+// halves so that the global loads of tile t+1 are in flight while tile t feeds the tensor pipe:
+//   tile_load : every warp-iteration loads 32 consecutive IQ samples (one 8-byte load per lane) into
+//               registers;
+//   tile_store: IQ-correct (WFM), take the neighbour from the previous lane, discriminate, store the
+//               31 outputs of the iteration.  Each sample is loaded and corrected once.
+template <int PF>
+__device__ __forceinline__ void tile_load(float2 (&pf)[PF], const float2* __restrict__ x, const int g0,
+                                          const int n_wi, const int N, const int warp, const int lane) {
+#pragma unroll
+    for (int it = 0; it < PF; ++it) {
+        const int wi = warp + it * (DEMOD_THREADS / 32);
+        const int gi = g0 + 31 * wi + lane;
+        pf[it] = make_float2(0.f, 0.f);
+        if (wi < n_wi && gi >= 0 && gi < N) pf[it] = __ldg(x + gi);
+    }
+}
+
+template <bool WFM, int PF>
+__device__ __forceinline__ void tile_store(float* __restrict__ buf, const float2 (&pf)[PF],
+                                           const float2* __restrict__ x, const int g0, const int E,
+                                           const int n_wi, const int N, const IqCorr k, const float scale,
+                                           const int warp, const int lane) {
+    const int L = N - 1;
+#pragma unroll
+    for (int it = 0; it < PF; ++it) {
+        const int wi = warp + it * (DEMOD_THREADS / 32);
+        float2 cur = pf[it];
+        if (WFM) cur = iq_apply(cur, k);
+        float2 prev;
+        prev.x = __shfl_up_sync(0xffffffffu, cur.x, 1);
+        prev.y = __shfl_up_sync(0xffffffffu, cur.y, 1);
+        const int e = 31 * wi + lane - 1;
+        const int g = g0 + e;
+        float d = disc_core<WFM>(cur, prev, scale);
+        if (g < 0 || g >= L) d = 0.f;
+        if (wi < n_wi && lane > 0 && e < E) buf[e] = d;
+    }
+    // tiles larger than PF iterations per warp (very large q): finish without the register prefetch
+    for (int wi = warp + PF * (DEMOD_THREADS / 32); wi < n_wi; wi += DEMOD_THREADS / 32) {
+        const int gi = g0 + 31 * wi + lane;
+        float2 cur = make_float2(0.f, 0.f);
+        if (gi >= 0 && gi < N) cur = __ldg(x + gi);
+        if (WFM) cur = iq_apply(cur, k);
+        float2 prev;
+        prev.x = __shfl_up_sync(0xffffffffu, cur.x, 1);
+        prev.y = __shfl_up_sync(0xffffffffu, cur.y, 1);
+        const int e = 31 * wi + lane - 1;
+        const int g = g0 + e;
+        float d = disc_core<WFM>(cur, prev, scale);
+        if (g < 0 || g >= L) d = 0.f;
+        if (lane > 0 && e < E) buf[e] = d;
+    }
 }
 
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, const double a, const double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1)
                  : "d"(a), "d"(b));
+}
+
+// One row of y = A x with x spread over the S lanes of a group (4 independent partial sums keep the
+// dependent fp64 chain short).
+template <int S>
+__device__ __forceinline__ double matvec_row(const double (&a)[S], const double x, const int lane_base) {
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+#pragma unroll
+    for (int c = 0; c < S; c += 4) {
+        p0 = fma(a[c], __shfl_sync(0xffffffffu, x, lane_base + c), p0);
+        p1 = fma(a[c + 1], __shfl_sync(0xffffffffu, x, lane_base + c + 1), p1);
+        p2 = fma(a[c + 2], __shfl_sync(0xffffffffu, x, lane_base + c + 2), p2);
+        p3 = fma(a[c + 3], __shfl_sync(0xffffffffu, x, lane_base + c + 3), p3);
+    }
+    return (p0 + p1) + (p2 + p3);
 }
 
 // x_{i+1} = A x_i + u_i, i = 0..n-1, over the slot field U[slot*rows + foff + r]; forward walks
@@ -100,10 +201,8 @@ __device__ void blocked_scan(double* U, const int rows, const int foff, const in
             const int i = i0 + s;
             const bool act = grp < n_units && i < n;
             const int slot = fwd ? 1 + i : n - i;
-            double acc = act ? U[slot * rows + foff + r] : 0.0;
-#pragma unroll
-            for (int c = 0; c < S; ++c) acc = fma(a[c], __shfl_sync(0xffffffffu, x, lane_base + c), acc);
-            x = acc;
+            const double u = act ? U[slot * rows + foff + r] : 0.0;
+            x = u + matvec_row<S>(a, x, lane_base);
             if (act) U[slot * rows + foff + r] = x;
         }
     }
@@ -119,10 +218,8 @@ __device__ void blocked_scan(double* U, const int rows, const int foff, const in
             const int ilast = b * B + B - 1;
             const bool more = ilast < n;          // a full block follows
             const int slot = fwd ? 1 + ilast : n - ilast;
-            double acc = (more && grp == 0) ? U[slot * rows + foff + r] : 0.0;
-#pragma unroll
-            for (int c = 0; c < S; ++c) acc = fma(ap[c], __shfl_sync(0xffffffffu, X, lane_base + c), acc);
-            X = acc;
+            const double u = (more && grp == 0) ? U[slot * rows + foff + r] : 0.0;
+            X = u + matvec_row<S>(ap, X, lane_base);
         }
     }
     __syncthreads();
@@ -133,17 +230,14 @@ __device__ void blocked_scan(double* U, const int rows, const int foff, const in
             const int i = i0 + s;
             const bool act = grp < n_units && i < n;
             const int slot = fwd ? 1 + i : n - i;
-            double acc = 0.0;
-#pragma unroll
-            for (int c = 0; c < S; ++c) acc = fma(a[c], __shfl_sync(0xffffffffu, z, lane_base + c), acc);
-            z = acc;
+            z = matvec_row<S>(a, z, lane_base);
             if (act) U[slot * rows + foff + r] += z;
         }
     }
     __syncthreads();
 }
 
-template <int SF>
+template <int SF, int T, int NBUF>
 __global__ void __launch_bounds__(DEMOD_THREADS, 2)
 demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __restrict__ audio,
                    const long long n_frames, double* __restrict__ U_global) {
@@ -161,7 +255,7 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
     double* U = D.U_in_smem ? reinterpret_cast<double*>(smem + D.off_U)
                             : U_global + (size_t)blockIdx.x * (D.U_bytes / 8);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int q = D.q, lead = D.lead, L = D.L, n_body = D.n_body, Kp = D.Kp, stride = D.stride;
+    const int q = D.q, lead = D.lead, L = D.L, n_body = D.n_body, Kp = D.Kp;
 
     if (D.tab_in_smem) {
         double* ts = reinterpret_cast<double*>(smem + D.off_tab);
@@ -174,13 +268,30 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
         IqCorr kc = {1.f, 1.f, 0.f, 1.f};
         if (WFM) {
             // second moments over the block (fp64 accumulation), then iq_correction's estimates
-            double sii = 0.0, sqq = 0.0, siq = 0.0;
-            for (int i = tid; i < D.N; i += DEMOD_THREADS) {
-                const float2 s = __ldg(x + i);
-                sii += (double)s.x * (double)s.x;
-                sqq += (double)s.y * (double)s.y;
-                siq += (double)s.x * (double)s.y;
+            // (per-thread float partials over N/256 samples, combined in fp64: the same order of
+            // rounding error as numpy's own float32 pairwise means at :52, :60, :61)
+            float fii[4] = {0.f, 0.f, 0.f, 0.f}, fqq[4] = {0.f, 0.f, 0.f, 0.f}, fiq[4] = {0.f, 0.f, 0.f, 0.f};
+            int i = tid;
+            for (; i + 15 * DEMOD_THREADS < D.N; i += 16 * DEMOD_THREADS) {
+                float2 v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = __ldg(x + i + u * DEMOD_THREADS);   // 16 loads in flight
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    fii[u & 3] = fmaf(v[u].x, v[u].x, fii[u & 3]);
+                    fqq[u & 3] = fmaf(v[u].y, v[u].y, fqq[u & 3]);
+                    fiq[u & 3] = fmaf(v[u].x, v[u].y, fiq[u & 3]);
+                }
             }
+            for (; i < D.N; i += DEMOD_THREADS) {
+                const float2 s = __ldg(x + i);
+                fii[0] = fmaf(s.x, s.x, fii[0]);
+                fqq[0] = fmaf(s.y, s.y, fqq[0]);
+                fiq[0] = fmaf(s.x, s.y, fiq[0]);
+            }
+            double sii = ((double)fii[0] + (double)fii[1]) + ((double)fii[2] + (double)fii[3]);
+            double sqq = ((double)fqq[0] + (double)fqq[1]) + ((double)fqq[2] + (double)fqq[3]);
+            double siq = ((double)fiq[0] + (double)fiq[1]) + ((double)fiq[2] + (double)fiq[3]);
             sii = warp_sum(sii);
             sqq = warp_sum(sqq);
             siq = warp_sum(siq);
@@ -209,8 +320,19 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
             __syncthreads();
         }
 
+        // ---- clear the state slots (the tile products are accumulated with atomics)
+        for (int i = tid; i < (n_body + 2) * ROWS; i += DEMOD_THREADS) U[i] = 0.0;
         // ---- head: ext[0..27] depends on d[0..27] only
         if (tid <= EDGE) dh[tid] = (double)discriminator<WFM>(x, tid, L, kc, D.scale);
+        const int n_tiles = (n_body + T - 1) / T;
+        const int E = (T - 1) * q + Kp;                          // samples one tile's windows touch
+        const int n_wi = (E + 30) / 31;                          // warp-iterations of 31 outputs each
+        constexpr int PF = T == 32 ? 16 : 8;
+        float2 pf[PF];
+        if (n_tiles > 0) {
+            tile_load<PF>(pf, x, 1 - lead, n_wi, D.N, warp, lane);
+            tile_store<WFM, PF>(tile, pf, x, 1 - lead, E, n_wi, D.N, kc, D.scale, warp, lane);
+        }
         __syncthreads();
         if (tid <= SF) {
             double acc = 0.0;
@@ -219,28 +341,22 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
             else red[24] = acc;                  // yf at ext index 27
         }
 
-        // ---- body chunks: discriminator tile -> DMMA against the response tables
-        const int n_tiles = (n_body + TILE_CHUNKS - 1) / TILE_CHUNKS;
+        // ---- body chunks: discriminator tile -> DMMA against the response tables.  The IQ loads of
+        // tile t+1 are issued before tile t is consumed by the tensor pipe; one barrier per tile.
         for (int tl = 0; tl < n_tiles; ++tl) {
-            const int j0 = 1 + tl * TILE_CHUNKS;
-            for (int c = warp; c < TILE_CHUNKS; c += DEMOD_THREADS / 32) {
-                const int j = j0 + c;
-                const int gbase = (j - 1) * q + 1 - lead;
-                float* rowp = tile + c * stride;
-                for (int i = lane; i < Kp; i += 32) {
-                    float v = 0.f;
-                    if (j <= n_body && i < q + lead) v = discriminator<WFM>(x, gbase + i, L, kc, D.scale);
-                    rowp[i] = v;
-                }
-            }
-            __syncthreads();
+            const int j0 = 1 + tl * T;
+            const float* cur = tile + (NBUF == 2 ? (tl & 1) * D.tile_floats : 0);
+            const int g_next = (j0 + T - 1) * q + 1 - lead;
+            const bool more = tl + 1 < n_tiles;
+            if (more) tile_load<PF>(pf, x, g_next, n_wi, D.N, warp, lane);
             {
-                const int mt = warp & 3, kg = warp >> 2;
-                const int ks0 = kg ? D.KS / 2 : 0, ks1 = kg ? D.KS : D.KS / 2;
+                const int MT = T / 8, NKG = (DEMOD_THREADS / 32) / MT;
+                const int mt = warp % MT, kg = warp / MT;
+                const int ks0 = (D.KS * kg) / NKG, ks1 = (D.KS * (kg + 1)) / NKG;
                 double acc[NT][2];
 #pragma unroll
                 for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-                const float* arow = tile + (mt * 8 + (lane >> 2)) * stride + (lane & 3);
+                const float* arow = cur + (mt * 8 + (lane >> 2)) * q + (lane & 3);
                 const double* bp = tab + lane;
 #pragma unroll 2
                 for (int ks = ks0; ks < ks1; ++ks) {
@@ -250,25 +366,20 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
                         dmma_m8n8k4(acc[nt][0], acc[nt][1], a, bp[(ks * NT + nt) * 32]);
                 }
                 const int j = j0 + mt * 8 + (lane >> 2);
-                double* us = U + (size_t)j * ROWS;
-                if (kg == 0 && j <= n_body) {
+                if (j <= n_body) {
+                    double* us = U + (size_t)j * ROWS;
 #pragma unroll
                     for (int nt = 0; nt < NT; ++nt) {
                         const int col = nt * 8 + 2 * (lane & 3);
-                        if (col < ROWS) us[col] = acc[nt][0];
-                        if (col + 1 < ROWS) us[col + 1] = acc[nt][1];
-                    }
-                }
-                __syncthreads();
-                if (kg == 1 && j <= n_body) {
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        const int col = nt * 8 + 2 * (lane & 3);
-                        if (col < ROWS) us[col] += acc[nt][0];
-                        if (col + 1 < ROWS) us[col + 1] += acc[nt][1];
+                        if (col < ROWS) atomicAdd(us + col, acc[nt][0]);
+                        if (col + 1 < ROWS) atomicAdd(us + col + 1, acc[nt][1]);
                     }
                 }
             }
+            if (NBUF == 1) __syncthreads();
+            if (more)
+                tile_store<WFM, PF>(tile + (NBUF == 2 ? ((tl + 1) & 1) * D.tile_floats : 0), pf, x, g_next, E, n_wi,
+                                    D.N, kc, D.scale, warp, lane);
             __syncthreads();
         }
 
@@ -372,8 +483,6 @@ static int create_decim(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
     const int win = D.q + D.lead;
     D.Kp = (win + 3) & ~3;
     D.KS = D.Kp / 4;
-    D.stride = D.Kp;
-    while (D.stride % 32 != 4) ++D.stride;
     // every block of the scans must fit one lane group
     if (D.Bf < 1 || D.Bb < 1) return PSS_ERR_ARG;
     if ((D.n_body + D.Bf - 1) / D.Bf > DEMOD_THREADS / D.SF) return PSS_ERR_ARG;
@@ -401,16 +510,28 @@ static int create_decim(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
     if ((rc = upload(ctx, pl, d->tail_T, (size_t)(D.SB + D.m_tail) * D.tail_len * 8, &p))) return rc; D.tailT = (const double*)p;
     if ((rc = upload(ctx, pl, d->tail_M, (size_t)(D.SB + D.m_tail) * D.SF * 8, &p))) return rc; D.tailM = (const double*)p;
 
-    // shared-memory layout: tile + misc always; table and state slots when they fit in 113 KB
+    // shared-memory layout: tile(s) + misc always; table and state slots when they fit in 113 KB.
+    // Preference: 32-chunk double-buffered tiles, then smaller / single-buffered ones.
     const size_t budget = 113 * 1024;
-    size_t tile_b = (size_t)TILE_CHUNKS * D.stride * 4;
-    if (tile_b < (size_t)D.tail_len * 4) tile_b = (size_t)D.tail_len * 4;
-    tile_b = (tile_b + 15) & ~(size_t)15;
     const size_t misc_b = ((size_t)(512 + 32 + 32 + 64 + D.n_out) * 8 + 15) & ~(size_t)15;
     const size_t tab_b = frag.size() * 8;
     D.U_bytes = (((size_t)(D.n_body + 2) * D.rows * 8) + 15) & ~(size_t)15;
+    const int cand[4][2] = {{32, 2}, {16, 2}, {32, 1}, {16, 1}};
+    int pick = -1;
+    for (int c = 0; c < 4 && pick < 0; ++c) {
+        size_t tf = (size_t)(cand[c][0] - 1) * D.q + D.Kp;
+        if (tf * cand[c][1] < (size_t)D.tail_len) tf = ((size_t)D.tail_len + cand[c][1] - 1) / cand[c][1];
+        tf = (tf + 3) & ~(size_t)3;
+        const size_t tot = tf * 4 * cand[c][1] + misc_b + tab_b + D.U_bytes;
+        if (tot <= budget || c == 3) {
+            pick = c;
+            D.T = cand[c][0];
+            D.nbuf = cand[c][1];
+            D.tile_floats = (int)tf;
+        }
+    }
     size_t used = 0;
-    D.off_tile = (int)used; used += tile_b;
+    D.off_tile = (int)used; used += (size_t)D.tile_floats * 4 * D.nbuf;
     D.off_misc = (int)used; used += misc_b;
     if (used > budget) return PSS_ERR_UNSUPPORTED;
     D.tab_in_smem = used + tab_b <= budget;
@@ -439,17 +560,25 @@ static int launch_decim(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64
             pl->U_scratch_bytes = need;
         }
     }
+#define DECIM_LAUNCH(SFv, Tv, NBv)                                                                         \
+    do {                                                                                                   \
+        auto k = demod_decim_kernel<SFv, Tv, NBv>;                                                         \
+        PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_bytes)); \
+        k<<<(unsigned)grid, DEMOD_THREADS, D.smem_bytes, ctx->stream>>>(D, (const float2*)iq, audio, n_frames, \
+                                                                         (double*)pl->U_scratch);          \
+    } while (0)
     if (D.SF == 8) {
-        auto k = demod_decim_kernel<8>;
-        PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_bytes));
-        k<<<(unsigned)grid, DEMOD_THREADS, D.smem_bytes, ctx->stream>>>(D, (const float2*)iq, audio, n_frames,
-                                                                         (double*)pl->U_scratch);
+        if (D.T == 32 && D.nbuf == 2) DECIM_LAUNCH(8, 32, 2);
+        else if (D.T == 16 && D.nbuf == 2) DECIM_LAUNCH(8, 16, 2);
+        else if (D.T == 32) DECIM_LAUNCH(8, 32, 1);
+        else DECIM_LAUNCH(8, 16, 1);
     } else {
-        auto k = demod_decim_kernel<16>;
-        PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_bytes));
-        k<<<(unsigned)grid, DEMOD_THREADS, D.smem_bytes, ctx->stream>>>(D, (const float2*)iq, audio, n_frames,
-                                                                          (double*)pl->U_scratch);
+        if (D.T == 32 && D.nbuf == 2) DECIM_LAUNCH(16, 32, 2);
+        else if (D.T == 16 && D.nbuf == 2) DECIM_LAUNCH(16, 16, 2);
+        else if (D.T == 32) DECIM_LAUNCH(16, 32, 1);
+        else DECIM_LAUNCH(16, 16, 1);
     }
+#undef DECIM_LAUNCH
     PSS_LAUNCH_CHECK(ctx);
     return PSS_OK;
 }
