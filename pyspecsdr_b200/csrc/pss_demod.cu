@@ -350,29 +350,49 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
             const bool more = tl + 1 < n_tiles;
             if (more) tile_load<PF>(pf, x, g_next, n_wi, D.N, warp, lane);
             {
-                const int MT = T / 8, NKG = (DEMOD_THREADS / 32) / MT;
-                const int mt = warp % MT, kg = warp / MT;
-                const int ks0 = (D.KS * kg) / NKG, ks1 = (D.KS * (kg + 1)) / NKG;
-                double acc[NT][2];
+                // work split over the 8 warps: a unit = (m-tile of 8 chunks, n-tile of 8 table rows)
+                // over the whole window.  MT*NT is 8 or 16 -> whole units per warp, plain stores.
+                // MT=4, NT=3 (NFM, 32-chunk tiles): n-tiles 0/1 whole, the last n-tile (it only
+                // carries the yf-forcing row) split in two K halves -> atomics on that one column.
+                constexpr int MT = T / 8, UNITS = MT * NT, NW = DEMOD_THREADS / 32;
+                constexpr bool SPLIT_LAST = (UNITS % NW) != 0 && MT == 4 && NT == 3;
+                constexpr int UPW = SPLIT_LAST ? 1 : (UNITS + NW - 1) / NW;      // whole units per warp
 #pragma unroll
-                for (int nt = 0; nt < NT; ++nt) acc[nt][0] = acc[nt][1] = 0.0;
-                const float* arow = cur + (mt * 8 + (lane >> 2)) * q + (lane & 3);
-                const double* bp = tab + lane;
-#pragma unroll 2
-                for (int ks = ks0; ks < ks1; ++ks) {
-                    const double a = (double)arow[4 * ks];
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt)
-                        dmma_m8n8k4(acc[nt][0], acc[nt][1], a, bp[(ks * NT + nt) * 32]);
-                }
-                const int j = j0 + mt * 8 + (lane >> 2);
-                if (j <= n_body) {
-                    double* us = U + (size_t)j * ROWS;
-#pragma unroll
-                    for (int nt = 0; nt < NT; ++nt) {
-                        const int col = nt * 8 + 2 * (lane & 3);
-                        if (col < ROWS) atomicAdd(us + col, acc[nt][0]);
-                        if (col + 1 < ROWS) atomicAdd(us + col + 1, acc[nt][1]);
+                for (int uu = 0; uu < UPW + (SPLIT_LAST ? 1 : 0); ++uu) {
+                    int mt, nt, ks0 = 0, ks1 = D.KS;
+                    bool atomic = false;
+                    if (SPLIT_LAST) {
+                        mt = warp % MT;
+                        if (uu == 0) nt = warp / MT;
+                        else {
+                            nt = 2;
+                            atomic = true;
+                            ks0 = (warp / MT) ? D.KS / 2 : 0;
+                            ks1 = (warp / MT) ? D.KS : D.KS / 2;
+                        }
+                    } else {
+                        const int unit = warp * UPW + uu;
+                        if (unit >= UNITS) break;
+                        mt = unit % MT;
+                        nt = unit / MT;
+                    }
+                    double c0 = 0.0, c1 = 0.0;
+                    const float* arow = cur + (mt * 8 + (lane >> 2)) * q + (lane & 3);
+                    const double* bp = tab + nt * 32 + lane;
+#pragma unroll 4
+                    for (int ks = ks0; ks < ks1; ++ks)
+                        dmma_m8n8k4(c0, c1, (double)arow[4 * ks], bp[ks * NT * 32]);
+                    const int j = j0 + mt * 8 + (lane >> 2);
+                    const int col = nt * 8 + 2 * (lane & 3);
+                    if (j <= n_body) {
+                        double* us = U + (size_t)j * ROWS;
+                        if (atomic) {
+                            if (col < ROWS) atomicAdd(us + col, c0);
+                            if (col + 1 < ROWS) atomicAdd(us + col + 1, c1);
+                        } else {
+                            if (col < ROWS) us[col] = c0;
+                            if (col + 1 < ROWS) us[col + 1] = c1;
+                        }
                     }
                 }
             }
