@@ -31,9 +31,19 @@ struct DecimDev {
     size_t smem_bytes, U_bytes;
 };
 
+struct FrameDevFwd {
+    int N = 0, n_taps = 0, n_sections = 0, C = 0, B = 0;
+    const float* taps = nullptr;
+    const double* sos = nullptr;
+    const double* AC = nullptr;
+    const double* ACB = nullptr;
+    size_t smem_bytes = 0;
+};
+
 struct pss_demod_plan {
     int kind = 0, mode = 0, N = 0, out_len = 0, channels = 1;
     DecimDev dec{};
+    FrameDevFwd frm{};
     std::vector<void*> dev_allocs;
     void* U_scratch = nullptr;
     size_t U_scratch_bytes = 0;
@@ -603,6 +613,319 @@ static int launch_decim(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64
     return PSS_OK;
 }
 
+
+// =================================================================================================
+// Frame kernels: AM (signal_processing.py:179-195), USB/LSB (:198-217), RAW (:237-238 + :46-80).
+// One CTA of 512 threads owns one block; the fp32 working row lives in shared memory, the block is
+// read from HBM once and the peak-normalised mono result written once.
+// =================================================================================================
+#define FRAME_THREADS 512
+#define FIR_MAX_TAPS 65
+
+typedef FrameDevFwd FrameDev;   // C = samples per thread-chunk (AM), B = scan block, AC/ACB [16][16] padded
+
+// ---- USB / LSB: y = lfilter(taps, 1, x).real (the hilbert() round trip is the identity on the real
+// part and both side-band branches are identical), / max|y| * 0.95.
+__global__ void __launch_bounds__(FRAME_THREADS, 1)
+demod_fir_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restrict__ audio, const long long n_frames) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    float* row = reinterpret_cast<float*>(smem) + 64;     // [-64 .. n_rounds*ROUND): zero history in front
+    __shared__ float taps_s[FIR_MAX_TAPS + 3];
+    __shared__ float redf[FRAME_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int N = D.N;
+    if (tid < FIR_MAX_TAPS) taps_s[tid] = tid < D.n_taps ? D.taps[tid] : 0.f;
+    constexpr int OUT_PER = 8, ROUND = FRAME_THREADS * OUT_PER;
+    const int n_rounds = (N + ROUND - 1) / ROUND;
+    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
+        const float2* x = iq + frame * N;
+        __syncthreads();
+        if (tid < 64) row[tid - 64] = 0.f;
+        for (int i = tid; i < n_rounds * ROUND; i += FRAME_THREADS) row[i] = i < N ? __ldg(x + i).x : 0.f;
+        __syncthreads();
+        float mx = 0.f;
+        // rounds walk the block from its end so the in-place overwrite never touches unread input
+        for (int r = n_rounds - 1; r >= 0; --r) {
+            const int n0 = r * ROUND + tid * OUT_PER;
+            float win[FIR_MAX_TAPS - 1 + 8];              // x[n0-64 .. n0+7]
+            const float4* w4 = reinterpret_cast<const float4*>(row + n0 - (FIR_MAX_TAPS - 1));
+#pragma unroll
+            for (int k = 0; k < (FIR_MAX_TAPS - 1 + 8) / 4; ++k) {
+                const float4 v = w4[k];
+                win[4 * k] = v.x; win[4 * k + 1] = v.y; win[4 * k + 2] = v.z; win[4 * k + 3] = v.w;
+            }
+            float acc[8];
+#pragma unroll
+            for (int o = 0; o < 8; ++o) acc[o] = 0.f;
+#pragma unroll
+            for (int k = 0; k < FIR_MAX_TAPS; ++k) {
+                const float h = taps_s[k];
+#pragma unroll
+                for (int o = 0; o < 8; ++o) acc[o] = fmaf(h, win[o + (FIR_MAX_TAPS - 1) - k], acc[o]);
+            }
+            __syncthreads();
+            *reinterpret_cast<float4*>(row + n0) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+            *reinterpret_cast<float4*>(row + n0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+#pragma unroll
+            for (int o = 0; o < 8; ++o)
+                if (n0 + o < N) mx = fmaxf(mx, fabsf(acc[o]));
+            __syncthreads();
+        }
+        mx = warp_max(mx);
+        if (lane == 0) redf[warp] = mx;
+        __syncthreads();
+        mx = redf[0];
+        for (int w = 1; w < FRAME_THREADS / 32; ++w) mx = fmaxf(mx, redf[w]);
+        float* dst = audio + frame * N;
+        for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = (float)((double)row[i] / (double)mx * 0.95);
+    }
+}
+
+// ---- AM: |x| - mean -> cascaded biquads (fp64 state, scipy sosfilt DF2T order, zero initial state)
+// -> / max|y| * 0.95.  The recurrence over the block is a chunked scan: every thread owns C
+// consecutive samples; pass A gives each chunk's zero-state response end state, a blocked scan of
+// the 2*n_sections-dimensional state over the chunks gives every chunk's true initial state, pass B
+// re-runs the chunk from it and emits the outputs.
+template <int NS>
+__device__ __forceinline__ double sos_step(const double (&c)[NS][5], double (&z)[NS][2], double v) {
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const double y = fma(c[s][0], v, z[s][0]);                    // b0*x + z0
+        z[s][0] = fma(-c[s][3], y, fma(c[s][1], v, z[s][1]));         // b1*x - a1*y + z1
+        z[s][1] = fma(-c[s][4], y, c[s][2] * v);                      // b2*x - a2*y
+        v = y;
+    }
+    return v;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(FRAME_THREADS, 1)
+demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restrict__ audio, const long long n_frames) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int N = D.N, C = D.C;
+    const int n_chunks = (N + C - 1) / C;                 // <= FRAME_THREADS
+    double* US = reinterpret_cast<double*>(smem);         // [(n_chunks + 2)][16] scan slots
+    double* XS = US + (size_t)(FRAME_THREADS + 2) * 16;   // [32][16]
+    double* redd = XS + 512;                              // [32]
+    float* row = reinterpret_cast<float*>(redd + 32);     // [N + N/C] skewed: idx + idx / C
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double c[NS][5];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        const double a0 = D.sos[s * 6 + 3];
+        c[s][0] = D.sos[s * 6 + 0] / a0;
+        c[s][1] = D.sos[s * 6 + 1] / a0;
+        c[s][2] = D.sos[s * 6 + 2] / a0;
+        c[s][3] = D.sos[s * 6 + 4] / a0;
+        c[s][4] = D.sos[s * 6 + 5] / a0;
+    }
+    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
+        const float2* x = iq + frame * N;
+        __syncthreads();
+        // envelope (float32 hypot like np.abs on complex64) and its mean
+        double sum = 0.0;
+        for (int i = tid; i < N; i += FRAME_THREADS) {
+            const float2 v = __ldg(x + i);
+            const float e = hypotf(v.x, v.y);
+            row[i + i / C] = e;
+            sum += (double)e;
+        }
+        for (int i = tid; i < (FRAME_THREADS + 2) * 16; i += FRAME_THREADS) US[i] = 0.0;
+        sum = warp_sum(sum);
+        if (lane == 0) redd[warp] = sum;
+        __syncthreads();
+        double tot = 0.0;
+        for (int w = 0; w < FRAME_THREADS / 32; ++w) tot += redd[w];
+        const float mean = (float)(tot / (double)N);                   // np.mean(envelope), float32
+        // pass A: zero-state response end state of every chunk
+        const int i0 = tid * C, i1 = min(N, i0 + C);
+        const float* rp = row + i0 + tid;                              // skew: i0 / C == tid
+        if (tid < n_chunks) {
+            double z[NS][2];
+#pragma unroll
+            for (int s = 0; s < NS; ++s) z[s][0] = z[s][1] = 0.0;
+            for (int i = 0; i < i1 - i0; ++i) sos_step<NS>(c, z, (double)__fsub_rn(rp[i], mean));
+            double* u = US + (size_t)(tid + 1) * 16;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                u[2 * s] = z[s][0];
+                u[2 * s + 1] = z[s][1];
+            }
+        }
+        __syncthreads();
+        // true state after every chunk: x_{c+1} = AC x_c + u_c, x_0 = 0 (slot 0 stays zero)
+        blocked_scan<16>(US, 16, 0, n_chunks, true, D.AC, D.ACB, D.B, US, XS, tid);
+        // pass B: re-run from the true initial state (slot tid = state after chunk tid-1), in place
+        float mx = 0.f;
+        if (tid < n_chunks) {
+            double z[NS][2];
+            const double* u = US + (size_t)tid * 16;
+#pragma unroll
+            for (int s = 0; s < NS; ++s) {
+                z[s][0] = u[2 * s];
+                z[s][1] = u[2 * s + 1];
+            }
+            float* wp = row + i0 + tid;
+            for (int i = 0; i < i1 - i0; ++i) {
+                const float y = (float)sos_step<NS>(c, z, (double)__fsub_rn(wp[i], mean));
+                wp[i] = y;
+                mx = fmaxf(mx, fabsf(y));
+            }
+        }
+        mx = warp_max(mx);
+        __syncthreads();
+        if (lane == 0) redd[warp] = (double)mx;
+        __syncthreads();
+        double m = redd[0];
+        for (int w = 1; w < FRAME_THREADS / 32; ++w) m = fmax(m, redd[w]);
+        float* dst = audio + frame * N;
+        for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = (float)((double)row[i + i / C] / m * 0.95);
+    }
+}
+
+// ---- RAW: real(iq_correction(x)) (signal_processing.py:46-80, :237-238), float32 like the reference
+__global__ void __launch_bounds__(256)
+demod_raw_kernel(const int N, const float2* __restrict__ iq, float* __restrict__ audio, const long long n_frames) {
+    __shared__ double red[5][8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
+        const float2* x = iq + frame * N;
+        double m[5] = {0, 0, 0, 0, 0};     // sum I, Q, I^2, Q^2, IQ
+        for (int i = tid; i < N; i += 256) {
+            const float2 v = __ldg(x + i);
+            const double a = v.x, b = v.y;
+            m[0] += a; m[1] += b; m[2] = fma(a, a, m[2]); m[3] = fma(b, b, m[3]); m[4] = fma(a, b, m[4]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            m[k] = warp_sum(m[k]);
+            if (lane == 0) red[k][warp] = m[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            double t = 0.0;
+            for (int w = 0; w < 8; ++w) t += red[k][w];
+            m[k] = t / (double)N;          // means
+        }
+        const double p_in = (m[2] + m[3]) - (m[0] * m[0] + m[1] * m[1]);          // var(x - mean)  :48-49
+        const float q_amp = (float)sqrt(2.0 * m[3]);                              // :52
+        const double qa = q_amp;
+        const float alpha = (float)sqrt(2.0 * m[2] / (qa * qa));                  // :60
+        const float sin_phi = (float)((2.0 / (double)alpha) * (m[4] / (qa * qa)));   // :61
+        const float cos_phi = sqrtf(1.f - sin_phi * sin_phi);                     // :64
+        const float inv_q = 1.f / q_amp, inv_a = 1.f / alpha, g = -sin_phi / alpha, inv_c = 1.f / cos_phi;
+        // corrected = (a1*I, a2*I + a3*Q); its variance from the input moments
+        const double a1 = (double)inv_q * inv_a * inv_c, a2 = (double)g * inv_q * inv_c, a3 = (double)inv_q * inv_c;
+        const double e2 = a1 * a1 * m[2] + a2 * a2 * m[2] + 2.0 * a2 * a3 * m[4] + a3 * a3 * m[3];
+        const double mr = a1 * m[0], mi = a2 * m[0] + a3 * m[1];
+        const float scale = (float)sqrt(p_in / (e2 - (mr * mr + mi * mi)));       // :80
+        float* dst = audio + frame * N;
+        for (int i = tid; i < N; i += 256) {
+            const float I = __ldg(x + i).x;
+            const float zr = __fmul_rn(I, inv_q);
+            dst[i] = __fmul_rn(__fmul_rn(__fmul_rn(inv_a, zr), inv_c), scale);
+        }
+    }
+}
+
+static int create_frame(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* pl) {
+    FrameDev& F = pl->frm;
+    F.N = d->N;
+    pl->out_len = d->N;
+    pl->channels = 1;
+    int rc;
+    const void* p;
+    if (d->kind == PSS_PLAN_RAW) return PSS_OK;
+    if (d->kind == PSS_PLAN_FIR) {
+        if (!d->taps || d->n_taps < 1 || d->n_taps > FIR_MAX_TAPS) return PSS_ERR_UNSUPPORTED;
+        std::vector<float> t(d->n_taps);
+        for (int i = 0; i < d->n_taps; ++i) t[i] = (float)d->taps[i];
+        if ((rc = upload(ctx, pl, t.data(), t.size() * 4, &p))) return rc;
+        F.taps = (const float*)p;
+        F.n_taps = d->n_taps;
+        const size_t round = (size_t)FRAME_THREADS * 8;
+        F.smem_bytes = (64 + ((size_t)d->N + round - 1) / round * round) * 4;
+        if (F.smem_bytes > 220 * 1024) return PSS_ERR_UNSUPPORTED;      // block too long for one CTA
+        return PSS_OK;
+    }
+    // SOS
+    if (!d->sos || d->n_sections < 1 || d->n_sections > 5) return PSS_ERR_UNSUPPORTED;
+    const int ns = d->n_sections;
+    F.n_sections = ns;
+    F.C = (d->N + FRAME_THREADS - 1) / FRAME_THREADS;
+    if (F.C < 1) F.C = 1;
+    const int n_chunks = (d->N + F.C - 1) / F.C;
+    F.B = (n_chunks + 31) / 32;
+    if (F.B < 1) F.B = 1;
+    // zero-input transition of one chunk, by stepping the cascade on unit states (padded to 16x16)
+    std::vector<double> AC(256, 0.0), ACB(256, 0.0), tmp(256, 0.0);
+    for (int col = 0; col < 2 * ns; ++col) {
+        std::vector<double> z(2 * ns, 0.0);
+        z[col] = 1.0;
+        for (int step = 0; step < F.C; ++step) {
+            double v = 0.0;
+            for (int s = 0; s < ns; ++s) {
+                const double* c = d->sos + s * 6;
+                const double y = (c[0] * v + z[2 * s] * c[3]) / c[3];
+                const double z0 = (c[1] * v - c[4] * y) / c[3] + z[2 * s + 1];
+                const double z1 = (c[2] * v - c[5] * y) / c[3];
+                z[2 * s] = z0;
+                z[2 * s + 1] = z1;
+                v = y;
+            }
+        }
+        for (int r = 0; r < 2 * ns; ++r) AC[r * 16 + col] = z[r];
+    }
+    ACB = AC;
+    for (int k = 1; k < F.B; ++k) {
+        for (int r = 0; r < 16; ++r)
+            for (int c2 = 0; c2 < 16; ++c2) {
+                double acc = 0.0;
+                for (int m = 0; m < 16; ++m) acc += AC[r * 16 + m] * ACB[m * 16 + c2];
+                tmp[r * 16 + c2] = acc;
+            }
+        ACB = tmp;
+    }
+    if ((rc = upload(ctx, pl, d->sos, (size_t)ns * 6 * 8, &p))) return rc; F.sos = (const double*)p;
+    if ((rc = upload(ctx, pl, AC.data(), 256 * 8, &p))) return rc; F.AC = (const double*)p;
+    if ((rc = upload(ctx, pl, ACB.data(), 256 * 8, &p))) return rc; F.ACB = (const double*)p;
+    F.smem_bytes = ((size_t)(FRAME_THREADS + 2) * 16 * 8 + 512 * 8 + 32 * 8 + ((size_t)d->N + d->N / F.C + 8) * 4 + 15) & ~(size_t)15;
+    if (F.smem_bytes > 220 * 1024) return PSS_ERR_UNSUPPORTED;
+    return PSS_OK;
+}
+
+static int launch_frame(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t n_frames, float* audio) {
+    FrameDev& F = pl->frm;
+    long long grid = ctx->sm_count;
+    if (pl->kind == PSS_PLAN_RAW) grid *= 4;
+    if (grid > n_frames) grid = n_frames;
+    if (pl->kind == PSS_PLAN_RAW) {
+        demod_raw_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(F.N, (const float2*)iq, audio, n_frames);
+    } else if (pl->kind == PSS_PLAN_FIR) {
+        PSS_CUDA(ctx, cudaFuncSetAttribute(demod_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.smem_bytes));
+        demod_fir_kernel<<<(unsigned)grid, FRAME_THREADS, F.smem_bytes, ctx->stream>>>(F, (const float2*)iq, audio, n_frames);
+    } else {
+#define SOS_LAUNCH(NSv)                                                                                         \
+    do {                                                                                                        \
+        auto k = demod_sos_kernel<NSv>;                                                                         \
+        PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.smem_bytes)); \
+        k<<<(unsigned)grid, FRAME_THREADS, F.smem_bytes, ctx->stream>>>(F, (const float2*)iq, audio, n_frames); \
+    } while (0)
+        switch (F.n_sections) {
+            case 1: SOS_LAUNCH(1); break;
+            case 2: SOS_LAUNCH(2); break;
+            case 3: SOS_LAUNCH(3); break;
+            case 4: SOS_LAUNCH(4); break;
+            default: SOS_LAUNCH(5); break;
+        }
+#undef SOS_LAUNCH
+    }
+    PSS_LAUNCH_CHECK(ctx);
+    return PSS_OK;
+}
+
 void pss_demod_release(pss_ctx*) {}
 
 extern "C" {
@@ -618,6 +941,8 @@ int pss_demod_plan_create(pss_ctx* ctx, const pss_demod_desc* desc, pss_demod_pl
     pl->N = desc->N;
     int rc = PSS_ERR_UNSUPPORTED;
     if (desc->kind == PSS_PLAN_DECIM) rc = create_decim(ctx, desc, pl);
+    else if (desc->kind == PSS_PLAN_FIR || desc->kind == PSS_PLAN_SOS || desc->kind == PSS_PLAN_RAW)
+        rc = create_frame(ctx, desc, pl);
     if (rc != PSS_OK) {
         pss_demod_plan_destroy(ctx, pl);
         return rc;
@@ -646,7 +971,7 @@ int pss_demod_c64_dev(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t
     if (!ctx || !pl || !iq || !audio || n_frames < 0) return PSS_ERR_ARG;
     if (n_frames == 0) return PSS_OK;
     if (pl->kind == PSS_PLAN_DECIM) return launch_decim(ctx, pl, iq, n_frames, audio);
-    return PSS_ERR_UNSUPPORTED;
+    return launch_frame(ctx, pl, iq, n_frames, audio);
 }
 
 int pss_demod_c64(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t n_frames, float* audio) {

@@ -60,3 +60,42 @@ def test_demod_scale_invariance_property(ctx):
     a = ctx.demod(x, 2.4e6, "NFM")
     b = ctx.demod((x * np.float32(0.25)).astype(np.complex64), 2.4e6, "NFM")
     assert rms(a, b.astype(np.float64)) <= TOL_RMS
+
+
+FRAME_CASES = [
+    ("AM", "am", 32768, 1e6), ("AM", "noise", 8192, 1e6), ("AM", "am", 5000, 1e6),
+    ("USB", "ssb", 32768, 1e6), ("LSB", "ssb", 8192, 1e6), ("USB", "noise", 4097, 1e6),
+    ("RAW", "tone40", 4096, 1e6), ("RAW", "noise", 32768, 2.4e6),
+]
+
+
+@pytest.mark.parametrize("mode,kind,n,fs", FRAME_CASES)
+def test_frame_demod_vs_oracle(ctx, mode, kind, n, fs):
+    x = np.stack([synth.make(kind, n, seed=30 + s) for s in range(3)])
+    if mode == "RAW":       # give iq_correction something to correct
+        x = (x * np.complex64(0.8 + 0.1j) + np.complex64(0.05 - 0.02j)).astype(np.complex64)
+    got = ctx.demod(x, fs, mode)
+    assert got.shape == (3, n, 1)
+    for f in range(len(x)):
+        ref = O.demod(x[f], fs, mode)
+        mono = ref[:, 0] if ref.ndim == 2 else ref
+        scale = 1.0 if mode != "RAW" else float(np.max(np.abs(mono)))
+        assert rms(got[f, :, 0], mono) <= TOL_RMS * scale, (mode, kind, n, rms(got[f, :, 0], mono))
+
+
+def test_frame_demod_golden(ctx, golden):
+    g = golden("demod")
+    for mode, kind, n, fs in [("AM", "am", 8192, 1e6), ("AM", "noise", 8192, 1e6), ("USB", "ssb", 8192, 1e6),
+                              ("LSB", "ssb", 8192, 1e6), ("USB", "noise", 4097, 1e6)]:
+        x = synth.make(kind, n, seed=11)
+        got = ctx.demod(x, fs, mode)[0, :, 0]
+        assert rms(got, g[f"{mode}_{kind}_{n}_{int(fs)}"]) <= TOL_RMS
+    x = synth.make("tone40", 4096, seed=11)
+    got = ctx.demod(x, 1e6, "RAW")[0, :, 0]
+    want = g["RAW_tone40_4096_1000000"]
+    assert rms(got, want) <= TOL_RMS * np.max(np.abs(want))
+
+
+def test_usb_equals_lsb_on_gpu(ctx):
+    x = synth.make("ssb", 8192, seed=4)
+    np.testing.assert_array_equal(ctx.demod(x, 1e6, "USB"), ctx.demod(x, 1e6, "LSB"))
