@@ -204,6 +204,20 @@ typedef struct {
 
 int pss_pipeline_c64(pss_ctx* ctx, const float* iq_host, int64_t n_blocks, const pss_pipeline_io* io);
 
+/* ------------------------------------------------------------------ helpers either side of the path
+ * pss_iq_correct_c64   iq_correction(samples)            signal_processing.py:46-80  -> complex64 out[n_frames][N]
+ * pss_sosfilt_f32      scipy sosfilt(sos, data), zero state, as used by bandpass_filter
+ *                                                        signal_processing.py:34-42  (sos designed by caller)
+ * pss_power_c64        measure_signal_power(samples)     signal_processing.py:325-328 -> dB per block
+ * pss_audio_to_int16   np.int16(samples * 32767)         audio_processing.py:36-38, io_manager.py:25-26
+ * Host pointers in and out.
+ */
+int pss_iq_correct_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, float* out);
+int pss_sosfilt_f32(pss_ctx* ctx, const float* x, int N, int64_t n_frames, const double* sos, int n_sections,
+                    float* y);
+int pss_power_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, float* power_db);
+int pss_audio_to_int16(pss_ctx* ctx, const float* audio, int64_t n, int16_t* pcm);
+
 #ifdef __cplusplus
 }
 #endif

@@ -64,6 +64,10 @@ def _signatures():
         "pss_display_render": (i32, [vp, vp, vp, i32, i64, i32, i64, i64, i64, i32, vp, vp]),
         "pss_display_render_dev": (i32, [vp, vp, vp, i32, i64, i32, i64, i64, i64, i32, vp, vp]),
         "pss_pipeline_c64": (i32, [vp, vp, i64, C.POINTER(PipelineIO)]),
+        "pss_iq_correct_c64": (i32, [vp, vp, i32, i64, vp]),
+        "pss_sosfilt_f32": (i32, [vp, vp, i32, i64, vp, i32, vp]),
+        "pss_power_c64": (i32, [vp, vp, i32, i64, vp]),
+        "pss_audio_to_int16": (i32, [vp, vp, i64, vp]),
         "pss_demod_plan_create": (i32, [vp, C.POINTER(DemodDesc), C.POINTER(vp)]),
         "pss_demod_plan_destroy": (None, [vp, vp]),
         "pss_demod_plan_out_len": (i32, [vp]),

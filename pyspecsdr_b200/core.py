@@ -261,3 +261,42 @@ class Context:
         import weakref
         weakref.finalize(raw, lib.pss_host_free, p)
         return arr
+
+    # ------------------------------------------------------------------ helpers either side of the path
+    def iq_correct(self, samples) -> np.ndarray:
+        """iq_correction (signal_processing.py:46-80) -> complex64, same shape as the input."""
+        x = np.ascontiguousarray(samples, dtype=np.complex64)
+        fr = x[None, :] if x.ndim == 1 else x
+        out = np.empty(fr.shape, np.complex64)
+        self._ck(lib.pss_iq_correct_c64(self._h, fr.ctypes.data, fr.shape[1], fr.shape[0], out.ctypes.data),
+                 "pss_iq_correct_c64")
+        return out[0] if x.ndim == 1 else out
+
+    def sosfilt(self, sos, data) -> np.ndarray:
+        """scipy.signal.sosfilt(sos, data) with zero initial state; float64 result like scipy."""
+        d = np.ascontiguousarray(data, dtype=np.float32)
+        fr = d[None, :] if d.ndim == 1 else d
+        sos = np.ascontiguousarray(sos, dtype=np.float64)
+        y = np.empty(fr.shape, np.float32)
+        self._ck(lib.pss_sosfilt_f32(self._h, fr.ctypes.data, fr.shape[1], fr.shape[0], sos.ctypes.data, len(sos),
+                                     y.ctypes.data), "pss_sosfilt_f32")
+        y = y.astype(np.float64)
+        return y[0] if d.ndim == 1 else y
+
+    def bandpass(self, data, lowcut, highcut, sample_rate) -> np.ndarray:
+        """bandpass_filter (signal_processing.py:34-42): design on the host with scipy, filter on the GPU."""
+        return self.sosfilt(filters.butter_sos(lowcut, highcut, sample_rate), data)
+
+    def signal_power(self, samples) -> np.ndarray:
+        """measure_signal_power (signal_processing.py:325-328) per block -> float32 dB."""
+        x = _as_frames(samples)
+        out = np.empty(len(x), np.float32)
+        self._ck(lib.pss_power_c64(self._h, x.ctypes.data, x.shape[1], x.shape[0], out.ctypes.data), "pss_power_c64")
+        return out
+
+    def to_int16(self, audio) -> np.ndarray:
+        """write_audio_samples' numeric line (audio_processing.py:36-38): np.int16(samples * 32767)."""
+        a = np.ascontiguousarray(audio, dtype=np.float32)
+        out = np.empty(a.shape, np.int16)
+        self._ck(lib.pss_audio_to_int16(self._h, a.ctypes.data, a.size, out.ctypes.data), "pss_audio_to_int16")
+        return out

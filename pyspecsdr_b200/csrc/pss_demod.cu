@@ -41,7 +41,7 @@ struct FrameDevFwd {
 };
 
 struct pss_demod_plan {
-    int kind = 0, mode = 0, N = 0, out_len = 0, channels = 1;
+    int kind = 0, mode = 0, N = 0, out_len = 0, channels = 1, plain = 0;
     DecimDev dec{};
     FrameDevFwd frm{};
     std::vector<void*> dev_allocs;
@@ -700,7 +700,8 @@ __device__ __forceinline__ double sos_step(const double (&c)[NS][5], double (&z)
 
 template <int NS>
 __global__ void __launch_bounds__(FRAME_THREADS, 1)
-demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restrict__ audio, const long long n_frames) {
+demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restrict__ audio, const long long n_frames,
+                 const int plain /* 1: input is a real float32 row, no envelope / mean / normalisation */) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int N = D.N, C = D.C;
     const int n_chunks = (N + C - 1) / C;                 // <= FRAME_THREADS
@@ -721,12 +722,18 @@ demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
     }
     for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
         const float2* x = iq + frame * N;
+        const float* xr = reinterpret_cast<const float*>(iq) + frame * N;
         __syncthreads();
         // envelope (float32 hypot like np.abs on complex64) and its mean
         double sum = 0.0;
         for (int i = tid; i < N; i += FRAME_THREADS) {
-            const float2 v = __ldg(x + i);
-            const float e = hypotf(v.x, v.y);
+            float e;
+            if (plain) {
+                e = __ldg(xr + i);
+            } else {
+                const float2 v = __ldg(x + i);
+                e = hypotf(v.x, v.y);
+            }
             row[i + i / C] = e;
             sum += (double)e;
         }
@@ -736,7 +743,7 @@ demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
         __syncthreads();
         double tot = 0.0;
         for (int w = 0; w < FRAME_THREADS / 32; ++w) tot += redd[w];
-        const float mean = (float)(tot / (double)N);                   // np.mean(envelope), float32
+        const float mean = plain ? 0.f : (float)(tot / (double)N);    // np.mean(envelope), float32
         // pass A: zero-state response end state of every chunk
         const int i0 = tid * C, i1 = min(N, i0 + C);
         const float* rp = row + i0 + tid;                              // skew: i0 / C == tid
@@ -779,13 +786,18 @@ demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
         double m = redd[0];
         for (int w = 1; w < FRAME_THREADS / 32; ++w) m = fmax(m, redd[w]);
         float* dst = audio + frame * N;
-        for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = (float)((double)row[i + i / C] / m * 0.95);
+        if (plain) {
+            for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = row[i + i / C];
+        } else {
+            for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = (float)((double)row[i + i / C] / m * 0.95);
+        }
     }
 }
 
 // ---- RAW: real(iq_correction(x)) (signal_processing.py:46-80, :237-238), float32 like the reference
 __global__ void __launch_bounds__(256)
-demod_raw_kernel(const int N, const float2* __restrict__ iq, float* __restrict__ audio, const long long n_frames) {
+demod_raw_kernel(const int N, const float2* __restrict__ iq, float* __restrict__ audio, const long long n_frames,
+                 const int complex_out /* 1: write the whole corrected complex64 block (iq_correction) */) {
     __shared__ double red[5][8];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
@@ -821,11 +833,22 @@ demod_raw_kernel(const int N, const float2* __restrict__ iq, float* __restrict__
         const double e2 = a1 * a1 * m[2] + a2 * a2 * m[2] + 2.0 * a2 * a3 * m[4] + a3 * a3 * m[3];
         const double mr = a1 * m[0], mi = a2 * m[0] + a3 * m[1];
         const float scale = (float)sqrt(p_in / (e2 - (mr * mr + mi * mi)));       // :80
-        float* dst = audio + frame * N;
-        for (int i = tid; i < N; i += 256) {
-            const float I = __ldg(x + i).x;
-            const float zr = __fmul_rn(I, inv_q);
-            dst[i] = __fmul_rn(__fmul_rn(__fmul_rn(inv_a, zr), inv_c), scale);
+        if (complex_out) {
+            float2* dst = reinterpret_cast<float2*>(audio) + frame * N;
+            for (int i = tid; i < N; i += 256) {
+                const float2 v = __ldg(x + i);
+                const float zr = __fmul_rn(v.x, inv_q), zi = __fmul_rn(v.y, inv_q);
+                const float i2 = __fmul_rn(inv_a, zr);
+                const float q2 = __fadd_rn(__fmul_rn(g, zr), zi);
+                dst[i] = make_float2(__fmul_rn(__fmul_rn(i2, inv_c), scale), __fmul_rn(__fmul_rn(q2, inv_c), scale));
+            }
+        } else {
+            float* dst = audio + frame * N;
+            for (int i = tid; i < N; i += 256) {
+                const float I = __ldg(x + i).x;
+                const float zr = __fmul_rn(I, inv_q);
+                dst[i] = __fmul_rn(__fmul_rn(__fmul_rn(inv_a, zr), inv_c), scale);
+            }
         }
     }
 }
@@ -902,7 +925,8 @@ static int launch_frame(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64
     if (pl->kind == PSS_PLAN_RAW) grid *= 4;
     if (grid > n_frames) grid = n_frames;
     if (pl->kind == PSS_PLAN_RAW) {
-        demod_raw_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(F.N, (const float2*)iq, audio, n_frames);
+        demod_raw_kernel<<<(unsigned)grid, 256, 0, ctx->stream>>>(F.N, (const float2*)iq, audio, n_frames,
+                                                                  pl->channels == 2 ? 1 : 0);
     } else if (pl->kind == PSS_PLAN_FIR) {
         PSS_CUDA(ctx, cudaFuncSetAttribute(demod_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.smem_bytes));
         demod_fir_kernel<<<(unsigned)grid, FRAME_THREADS, F.smem_bytes, ctx->stream>>>(F, (const float2*)iq, audio, n_frames);
@@ -911,7 +935,8 @@ static int launch_frame(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64
     do {                                                                                                        \
         auto k = demod_sos_kernel<NSv>;                                                                         \
         PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.smem_bytes)); \
-        k<<<(unsigned)grid, FRAME_THREADS, F.smem_bytes, ctx->stream>>>(F, (const float2*)iq, audio, n_frames); \
+        k<<<(unsigned)grid, FRAME_THREADS, F.smem_bytes, ctx->stream>>>(F, (const float2*)iq, audio, n_frames, \
+                                                                        pl->plain);                             \
     } while (0)
         switch (F.n_sections) {
             case 1: SOS_LAUNCH(1); break;
@@ -988,6 +1013,51 @@ int pss_demod_c64(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t n_f
     PSS_CUDA(ctx, cudaMemcpyAsync(audio, ctx->d_out, out_b, cudaMemcpyDeviceToHost, ctx->stream));
     PSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PSS_OK;
+}
+
+
+// ---- helpers outside the main loop's hot path, same kernels -------------------------------------
+int pss_iq_correct_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, float* out) {
+    if (!ctx || !iq || !out || N < 2 || n_frames < 0) return PSS_ERR_ARG;
+    pss_demod_desc d{};
+    d.kind = PSS_PLAN_RAW;
+    d.mode = PSS_MODE_RAW;
+    d.N = N;
+    pss_demod_plan* pl = nullptr;
+    int rc = pss_demod_plan_create(ctx, &d, &pl);
+    if (rc) return rc;
+    pl->channels = 2;
+    rc = pss_demod_c64(ctx, pl, iq, n_frames, out);
+    pss_demod_plan_destroy(ctx, pl);
+    return rc;
+}
+
+int pss_sosfilt_f32(pss_ctx* ctx, const float* x, int N, int64_t n_frames, const double* sos, int n_sections,
+                    float* y) {
+    if (!ctx || !x || !y || !sos || N < 1 || n_frames < 0) return PSS_ERR_ARG;
+    if (n_frames == 0) return PSS_OK;
+    pss_demod_desc d{};
+    d.kind = PSS_PLAN_SOS;
+    d.mode = PSS_MODE_AM;
+    d.N = N;
+    d.sos = sos;
+    d.n_sections = n_sections;
+    pss_demod_plan* pl = nullptr;
+    int rc = pss_demod_plan_create(ctx, &d, &pl);
+    if (rc) return rc;
+    pl->plain = 1;
+    PSS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t b = (size_t)n_frames * N * 4;
+    if (!(rc = pss_reserve(ctx, &ctx->d_in, &ctx->d_in_bytes, b)) && !(rc = pss_reserve(ctx, &ctx->d_out, &ctx->d_out_bytes, b))) {
+        cudaMemcpyAsync(ctx->d_in, x, b, cudaMemcpyHostToDevice, ctx->stream);
+        rc = pss_demod_c64_dev(ctx, pl, (const float*)ctx->d_in, n_frames, (float*)ctx->d_out);
+        if (!rc) {
+            cudaMemcpyAsync(y, ctx->d_out, b, cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = PSS_ERR_CUDA;
+        }
+    }
+    pss_demod_plan_destroy(ctx, pl);
+    return rc;
 }
 
 }  // extern "C"
