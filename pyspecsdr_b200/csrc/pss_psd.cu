@@ -29,6 +29,7 @@ struct PsdParams {
     int* count;
     int use_abs;
     float thr;
+    const void* ystage;   // second stage of a large transform: cx<T> rows [n_frames][N] (LOG2N1 > 0)
 };
 
 template <int LOG2N, typename T>
@@ -83,7 +84,9 @@ __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<
     if constexpr (P != NP - 1) __syncthreads();
 }
 
-template <int LOG2N, typename T, int EPI>
+// LOG2N1 > 0: this launch is the second stage of a length N*2^LOG2N1 transform (four-step FFT): frame
+// index = big_frame * N1 + k1, input = column-transformed, twiddled fp64 rows, output bin = k1 + N1*k2.
+template <int LOG2N, typename T, int EPI, int LOG2N1 = 0>
 __global__ void __launch_bounds__(PsdCfg<LOG2N, T>::THREADS, PsdCfg<LOG2N, T>::MINB)
 psd_kernel(const PsdParams p) {
     using C = PsdCfg<LOG2N, T>;
@@ -118,17 +121,23 @@ psd_kernel(const PsdParams p) {
     // ---- pass 0: global (coalesced 8-byte loads) * window -> radix-16 -> shared
     {
         cx<T> v[16];
-        const float2* src = p.iq + frame * N;
-        const T* win = reinterpret_cast<const T*>(p.window);
+        if constexpr (LOG2N1 > 0) {
+            const cx<T>* src = reinterpret_cast<const cx<T>*>(p.ystage) + frame * N;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) {
-            const int idx = t + r * TPF;
-            const float2 s = live ? __ldg(src + idx) : make_float2(0.f, 0.f);
-            if (win) {
-                const T w = __ldg(win + idx);
-                v[r] = {(T)s.x * w, (T)s.y * w};
-            } else {
-                v[r] = {(T)s.x, (T)s.y};
+            for (int r = 0; r < 16; ++r) v[r] = live ? src[t + r * TPF] : cx<T>{(T)0, (T)0};
+        } else {
+            const float2* src = p.iq + frame * N;
+            const T* win = reinterpret_cast<const T*>(p.window);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) {
+                const int idx = t + r * TPF;
+                const float2 s = live ? __ldg(src + idx) : make_float2(0.f, 0.f);
+                if (win) {
+                    const T w = __ldg(win + idx);
+                    v[r] = {(T)s.x * w, (T)s.y * w};
+                } else {
+                    v[r] = {(T)s.x, (T)s.y};
+                }
             }
         }
         fft_regs<16, T>::run(v);
@@ -143,7 +152,12 @@ psd_kernel(const PsdParams p) {
         const double pw = (double)X.x * (double)X.x + ((double)X.y * (double)X.y + 1e-10);
         const float d = db_from_power(pw);
         const int pos = k ^ (N >> 1);
-        if constexpr (EPI == EPI_RAW) {
+        if constexpr (LOG2N1 > 0) {
+            const long long fb = frame >> LOG2N1;
+            const int bin = (int)(frame & ((1 << LOG2N1) - 1)) + (k << LOG2N1);
+            const int ntot = N << LOG2N1;
+            if (live) p.db[fb * ntot + (bin ^ (ntot >> 1))] = d;
+        } else if constexpr (EPI == EPI_RAW) {
             if (live) p.db[frame * N + pos] = d;
         } else {
             row[pos] = d;
@@ -397,6 +411,199 @@ psd_kernel(const PsdParams p) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------- large transforms
+// N = N1 * N2 (N1 = 4, 8, 16; N2 = 4096 or 8192), four-step FFT:
+//   stage A (this kernel): per column n2, window, N1-point DFT over the stride-N2 samples held in
+//   registers, twiddle W_N^(n2*k1), fp64 rows Y[frame][k1][n2] to a scratch that is sized to stay in L2;
+//   stage B: psd_kernel<LOG2N2, T, EPI_RAW, LOG2N1> on every row, bins k1 + N1*k2.
+template <int LOG2N1, typename T>
+__global__ void __launch_bounds__(256)
+psd_colfft_kernel(const float2* __restrict__ iq, const T* __restrict__ window, const cx<T>* __restrict__ twN,
+                  const int N2, const long long n_frames, cx<T>* __restrict__ Y) {
+    constexpr int N1 = 1 << LOG2N1;
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long frame = gid / N2;
+    const int n2 = (int)(gid - frame * N2);
+    if (frame >= n_frames) return;
+    const long long N = (long long)N1 * N2;
+    const float2* src = iq + frame * N + n2;
+    cx<T> v[N1];
+#pragma unroll
+    for (int n1 = 0; n1 < N1; ++n1) {
+        const float2 s = __ldg(src + (long long)n1 * N2);
+        if (window) {
+            const T w = __ldg(window + (long long)n1 * N2 + n2);
+            v[n1] = {(T)s.x * w, (T)s.y * w};
+        } else {
+            v[n1] = {(T)s.x, (T)s.y};
+        }
+    }
+    fft_regs<N1, T>::run(v);
+    cx<T> o[N1];
+#pragma unroll
+    for (int q = 0; q < N1; ++q) o[fft_perm<N1>(q)] = v[q];
+    twiddle_apply<N1, T>(o, twN[n2]);                      // o[k1] *= W_N^(n2*k1)
+    cx<T>* dst = Y + frame * N + n2;
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) dst[(long long)k1 * N2] = o[k1];
+}
+
+// Row epilogue for rows that do not fit one CTA's shared memory: the same 5-bin smoothing, exact
+// median clamp, statistics and W-column resample as EPI_SMOOTH, streaming the row from L2.
+__global__ void __launch_bounds__(512)
+row_epilogue_kernel(const float* __restrict__ raw, const int N, const long long n_frames, float* __restrict__ db,
+                    float* __restrict__ cols, const int W, float* __restrict__ stats) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned us[8];
+    __shared__ double dsum[16];
+    __shared__ float fmx[16], fmn[16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = N - 4;
+    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const float* d = raw + f * N;
+        float* s = db + f * n;
+        if (tid < 8) us[tid] = (tid == 0 || tid == 5) ? 0xffffffffu : 0u;
+        __syncthreads();
+        unsigned kmin = 0xffffffffu, kmax = 0u;
+        bool has_nan = false;
+        for (int i = tid; i < n; i += 512) {
+            const float v = ((d[i] + d[i + 1]) + (d[i + 2] + d[i + 3]) + d[i + 4]) * 0.2f;
+            s[i] = v;
+            const unsigned k = f2key(v);
+            kmin = min(kmin, k);
+            kmax = max(kmax, k);
+            has_nan |= (v != v);
+        }
+        kmin = __reduce_min_sync(0xffffffffu, kmin);
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        if (lane == 0) {
+            atomicMin(&us[0], kmin);
+            atomicMax(&us[1], kmax);
+        }
+        if (__any_sync(0xffffffffu, has_nan) && lane == 0) atomicOr(&us[6], 1u);
+        __syncthreads();
+        kmin = us[0];
+        kmax = us[1];
+        const int common = min(__clz((int)(kmin ^ kmax)), 31);
+        unsigned rank = (unsigned)((n - 1) / 2), prefix = 0u;
+        for (int ps = 0; ps < 4; ++ps) {
+            const int shift = 24 - 8 * ps;
+            if (tid < 256) hist[tid] = 0u;
+            __syncthreads();
+            for (int i = tid; i < n; i += 512) {
+                const unsigned k = (f2key(s[i]) - kmin) << common;
+                if (ps == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (warp == 0) {
+                unsigned c[8], sum = 0;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    c[q] = hist[8 * lane + q];
+                    sum += c[q];
+                }
+                unsigned incl = sum;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += up;
+                }
+                const unsigned hit = __ballot_sync(0xffffffffu, incl > rank);
+                const int Ln = __ffs(hit) - 1;
+                if (lane == Ln) {
+                    unsigned r = rank - (incl - sum);
+                    int dg = 0;
+                    bool found = false;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (!found) {
+                            if (r < c[q]) { dg = q; found = true; }
+                            else r -= c[q];
+                        }
+                    }
+                    us[2] = (unsigned)(8 * lane + dg);
+                    us[3] = r;
+                }
+            }
+            __syncthreads();
+            prefix = (prefix << 8) | us[2];
+            rank = us[3];
+        }
+        const unsigned key1n = prefix;
+        unsigned cnt_le = 0, min_gt = 0xffffffffu;
+        for (int i = tid; i < n; i += 512) {
+            const unsigned k = (f2key(s[i]) - kmin) << common;
+            cnt_le += k <= key1n;
+            if (k > key1n) min_gt = min(min_gt, k);
+        }
+        cnt_le = __reduce_add_sync(0xffffffffu, cnt_le);
+        min_gt = __reduce_min_sync(0xffffffffu, min_gt);
+        if (lane == 0) {
+            atomicAdd(&us[4], cnt_le);
+            atomicMin(&us[5], min_gt);
+        }
+        __syncthreads();
+        float thr;
+        {
+            const unsigned key2n = ((n & 1) || us[4] > (unsigned)(n / 2)) ? key1n : us[5];
+            const float v1 = key2f((key1n >> common) + kmin), v2 = key2f((key2n >> common) + kmin);
+            thr = (float)(0.5 * ((double)v1 + (double)v2) - 10.0);
+            if (us[6]) thr = __int_as_float(0x7fc00000);
+        }
+        float mx = -INFINITY, mn = INFINITY;
+        double sm = 0.0;
+        for (int i = tid; i < n; i += 512) {
+            float v = s[i];
+            if (v < thr) v = thr;
+            s[i] = v;
+            mx = fmaxf(mx, v);
+            mn = fminf(mn, v);
+            sm += (double)v;
+        }
+        mx = warp_max(mx);
+        mn = warp_min(mn);
+        sm = warp_sum(sm);
+        if (lane == 0) {
+            fmx[warp] = mx;
+            fmn[warp] = mn;
+            dsum[warp] = sm;
+        }
+        __syncthreads();                       // also orders the clamped row for the resample below
+        if (stats && tid == 0) {
+            float a = fmx[0], b = fmn[0];
+            double t = dsum[0];
+            for (int w = 1; w < 16; ++w) {
+                a = fmaxf(a, fmx[w]);
+                b = fminf(b, fmn[w]);
+                t += dsum[w];
+            }
+            const float nanv = __int_as_float(0x7fc00000);
+            float4 st;
+            st.x = us[6] ? nanv : a;
+            st.y = us[6] ? nanv : (float)(t / n);
+            st.z = b;
+            st.w = a;
+            reinterpret_cast<float4*>(stats)[f] = st;
+        }
+        if (cols) {
+            const double step = W > 1 ? (double)(n - 1) / (double)(W - 1) : 0.0;
+            for (int c = tid; c < W; c += 512) {
+                const double x = (c == W - 1 && W > 1) ? (double)(n - 1) : c * step;
+                const int j = (int)x;
+                float o;
+                if (j >= n - 1) o = s[n - 1];
+                else {
+                    const double y0 = s[j], y1 = s[j + 1];
+                    o = (float)((y1 - y0) * (x - (double)j) + y0);
+                }
+                cols[f * W + c] = o;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------------------------- host side
 template <typename T>
 static int build_tables(pss_ctx* ctx, int log2n, pss_fft_tables& tab) {
@@ -484,6 +691,102 @@ static int get_tables(pss_ctx* ctx, int log2n, pss_fft_tables** out) {
     return PSS_OK;
 }
 
+
+// Large transforms: N = 2^log2n with 14 <= log2n <= 17.
+struct LargeTables {
+    void* twN = nullptr;           // cx<double>[N2]: W_N^n2
+    void* window[3] = {nullptr, nullptr, nullptr};
+};
+static std::map<int, LargeTables> g_large_tables[16];
+
+template <int LOG2N2, int LOG2N1>
+static int launch_stage_b(pss_ctx* ctx, const PsdParams& p) {
+    using C = PsdCfg<LOG2N2, double>;
+    auto kern = psd_kernel<LOG2N2, double, EPI_RAW, LOG2N1>;
+    PSS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+    const long long grid = (p.n_frames + C::FPC - 1) / C::FPC;
+    kern<<<(unsigned)grid, C::THREADS, C::SMEM, ctx->stream>>>(p);
+    PSS_LAUNCH_CHECK(ctx);
+    return PSS_OK;
+}
+
+static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames, int window, int epilogue,
+                     const pss_psd_out* out) {
+    const int log2n2 = log2n == 17 ? 13 : 12;
+    const int log2n1 = log2n - log2n2;
+    if (log2n1 < 2 || log2n1 > 4) return PSS_ERR_UNSUPPORTED;
+    const long long N = 1LL << log2n, N2 = 1LL << log2n2;
+    int rc;
+    pss_fft_tables* tab2;
+    if ((rc = get_tables(ctx, log2n2, &tab2))) return rc;
+    LargeTables& lt = g_large_tables[ctx->device & 15][log2n];
+    if (!lt.twN) {
+        std::vector<cx<double>> tw(N2);
+        std::vector<double> w(N);
+        const long double PI = 3.14159265358979323846264338327950288L;
+        for (long long k = 0; k < N2; ++k) {
+            const long double a = -2.0L * PI * (long double)k / (long double)N;
+            tw[k] = {(double)cosl(a), (double)sinl(a)};
+        }
+        PSS_CUDA(ctx, cudaMalloc(&lt.twN, N2 * sizeof(cx<double>)));
+        PSS_CUDA(ctx, cudaMemcpy(lt.twN, tw.data(), N2 * sizeof(cx<double>), cudaMemcpyHostToDevice));
+        for (int kind = PSS_WINDOW_HAMMING; kind <= PSS_WINDOW_HANN; ++kind) {
+            const long double a = kind == PSS_WINDOW_HAMMING ? 0.54L : 0.5L, b = kind == PSS_WINDOW_HAMMING ? 0.46L : 0.5L;
+            for (long long i = 0; i < N; ++i) w[i] = (double)(a - b * cosl(2.0L * PI * (long double)i / (long double)(N - 1)));
+            PSS_CUDA(ctx, cudaMalloc(&lt.window[kind], N * sizeof(double)));
+            PSS_CUDA(ctx, cudaMemcpy(lt.window[kind], w.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+        }
+    }
+    // scratch: fp64 rows of a sub-batch (kept <= 64 MB so it lives in L2) and, with an epilogue, the raw rows
+    long long sub = (64LL << 20) / (N * 16);
+    if (sub < 1) sub = 1;
+    if (sub > n_frames) sub = n_frames;
+    if ((rc = pss_reserve(ctx, &ctx->p_buf[7], &ctx->p_bytes[7], (size_t)sub * N * 16))) return rc;
+    float* raw = out->db;
+    if (epilogue == PSS_EPI_SMOOTH_CLAMP) {
+        if ((rc = pss_reserve(ctx, &ctx->p_buf[9], &ctx->p_bytes[9], (size_t)sub * N * 4))) return rc;
+        raw = (float*)ctx->p_buf[9];
+    }
+    const long long n_out = epilogue == PSS_EPI_SMOOTH_CLAMP ? N - 4 : N;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += sub) {
+        const long long nf = n_frames - f0 < sub ? n_frames - f0 : sub;
+        const float2* src = reinterpret_cast<const float2*>(iq) + f0 * N;
+        const double* win = window == PSS_WINDOW_NONE ? nullptr : (const double*)lt.window[window];
+        const long long threads = nf * N2;
+        const unsigned grid = (unsigned)((threads + 255) / 256);
+        cx<double>* Y = (cx<double>*)ctx->p_buf[7];
+        if (log2n1 == 2) psd_colfft_kernel<2, double><<<grid, 256, 0, ctx->stream>>>(src, win, (const cx<double>*)lt.twN, (int)N2, nf, Y);
+        else if (log2n1 == 3) psd_colfft_kernel<3, double><<<grid, 256, 0, ctx->stream>>>(src, win, (const cx<double>*)lt.twN, (int)N2, nf, Y);
+        else psd_colfft_kernel<4, double><<<grid, 256, 0, ctx->stream>>>(src, win, (const cx<double>*)lt.twN, (int)N2, nf, Y);
+        PSS_LAUNCH_CHECK(ctx);
+        PsdParams p{};
+        p.tw = tab2->twiddle;
+        p.ystage = Y;
+        p.n_frames = nf << log2n1;
+        p.db = epilogue == PSS_EPI_SMOOTH_CLAMP ? raw : out->db + f0 * N;
+        if (log2n2 == 13) rc = launch_stage_b<13, 4>(ctx, p);
+        else if (log2n1 == 2) rc = launch_stage_b<12, 2>(ctx, p);
+        else if (log2n1 == 3) rc = launch_stage_b<12, 3>(ctx, p);
+        else rc = launch_stage_b<12, 4>(ctx, p);
+        if (rc) return rc;
+        if (epilogue == PSS_EPI_SMOOTH_CLAMP) {
+            // the smoothed row is always produced (median/clamp work on it); use scratch when the caller
+            // does not want it
+            float* dbo = out->db ? out->db + f0 * n_out : nullptr;
+            if (!dbo) {
+                if ((rc = pss_reserve(ctx, &ctx->p_buf[8], &ctx->p_bytes[8], (size_t)sub * n_out * 4))) return rc;
+                dbo = (float*)ctx->p_buf[8];
+            }
+            const unsigned g2 = (unsigned)(nf < 2LL * ctx->sm_count ? nf : 2LL * ctx->sm_count);
+            row_epilogue_kernel<<<g2, 512, 0, ctx->stream>>>(raw, (int)N, nf, dbo,
+                                                            out->cols ? out->cols + f0 * out->W : nullptr, out->W,
+                                                            out->stats ? out->stats + f0 * 4 : nullptr);
+            PSS_LAUNCH_CHECK(ctx);
+        }
+    }
+    return PSS_OK;
+}
+
 // Device-pointer PSD; see pss.h.
 extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, int window,
                                int epilogue, int precision, const pss_psd_out* out) {
@@ -498,6 +801,7 @@ extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_f
     if (log2n < 0) return PSS_ERR_UNSUPPORTED;
     if (n_frames == 0) return PSS_OK;
     if (n_frames > 0x7fffffffLL) return PSS_ERR_ARG;
+    if (log2n > 13) return psd_large(ctx, iq, log2n, n_frames, window, epilogue, out);
     pss_fft_tables* tab;
     int rc = get_tables(ctx, log2n, &tab);
     if (rc != PSS_OK) return rc;

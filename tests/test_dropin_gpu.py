@@ -24,10 +24,11 @@ def test_exports_match_reference_namespace(sp):
     assert sp.DEFAULT_SAMPLE_RATE == 22050 and sp.BUTTER_ORDER == 5
 
 
-def test_compute_fft(sp):
-    x = synth.make("tone60", 4096, seed=1)
+@pytest.mark.parametrize("n", [4096, 8192, 32768])      # 32768 = the app's default read, pyspecsdr.py:105,2236
+def test_compute_fft(sp, n):
+    x = synth.make("tone60", n, seed=1)
     y = sp.compute_fft(x)
-    assert y.dtype == np.float64 and y.shape == (4096,)
+    assert y.dtype == np.float64 and y.shape == (n,)
     assert np.max(np.abs(y - O.psd_db(x))) <= 1e-4
 
 

@@ -115,3 +115,37 @@ def test_scanner_vs_oracle_and_golden(ctx, golden):
     for k in range(len(fr)):
         db = O.psd_db(fr[k], window="none")
         assert int(np.sum(db > -40 + 2 * TOL_DB)) <= count[k] <= int(np.sum(db > -40 - 2 * TOL_DB))
+
+
+@pytest.mark.parametrize("n", [16384, 32768, 65536, 131072])
+def test_psd_large_vs_oracle(ctx, n):
+    # four-step path (column DFTs -> fp64 rows in an L2-sized scratch -> row FFTs)
+    x = np.stack([synth.make(k, n, seed=n % 11 + i) for i, k in enumerate(("tone60", "wbfm", "noise"))])
+    got = ctx.psd(x, window="hamming")["db"]
+    assert np.max(np.abs(got - O.psd_db(x))) <= TOL_DB
+    got = ctx.psd(x[:1], window="none")["db"]
+    assert np.max(np.abs(got - O.psd_db(x[:1], window="none"))) <= TOL_DB
+
+
+@pytest.mark.parametrize("n", [16384, 32768])
+def test_psd_large_epilogue_vs_oracle(ctx, n):
+    x = np.stack([synth.make(k, n, seed=5 + i) for i, k in enumerate(("tone40", "wbfm"))])
+    W = 200
+    res = ctx.psd(x, epilogue=True, W=W, want_stats=True)
+    for f in range(len(x)):
+        want = O.psd_epilogue(O.psd_db(x[f]))
+        assert np.max(np.abs(res["db"][f] - want)) <= TOL_DB
+        assert np.max(np.abs(res["cols"][f] - O.resample_cols(want, W))) <= TOL_DB
+        pk, av = O.peak_avg(want)
+        assert abs(res["stats"][f][0] - pk) <= TOL_DB and abs(res["stats"][f][1] - av) <= TOL_DB
+    # more frames than one L2-sized sub-batch of the fp64 scratch
+    many = np.tile(x[:1], (150, 1))
+    got = ctx.psd(many, window="hamming")["db"]
+    assert np.all(got == got[0])
+
+
+def test_psd_golden_16384(ctx, golden):
+    g = golden("psd")
+    for kind in ("tone60", "wbfm"):
+        x = synth.make(kind, 16384, seed=16384 % 97)
+        assert np.max(np.abs(ctx.psd(x)["db"][0] - g[f"{kind}_16384"])) <= TOL_DB
