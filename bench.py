@@ -153,12 +153,12 @@ class ClockSampler:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="WFM", choices=["WFM", "NFM"])
     ap.add_argument("--blocks", type=int, default=4096, help="32768-sample blocks per GPU per step (4096 = 1 GiB)")
-    ap.add_argument("--cpu-blocks", type=int, default=384, help="blocks in the bounded CPU sample")
+    ap.add_argument("--cpu-blocks", type=int, default=1536, help="blocks in the bounded CPU sample")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -176,6 +176,7 @@ def main():
         if rank != 0:
             return
         cores = os.cpu_count() or 1
+        args.cpu_blocks = min(args.cpu_blocks, 512)        # keeps K steps within a few minutes on any host
         blocks = make_blocks_numpy(args.cpu_blocks, seed=0)
         for _ in range(max(args.warmup, 0) and 1):
             cpu_reference(blocks[:cores], args.mode)

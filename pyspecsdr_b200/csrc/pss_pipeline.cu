@@ -1,5 +1,37 @@
 // pss_pipeline_c64: one batched main-loop iteration with host buffers (include/pss.h).
+//
+// The batch is cut into chunks of blocks; chunk i+1's host->device copy, chunk i's kernels and chunk
+// i-1's device->host copies run concurrently on three streams (PCIe is full duplex, the copy engines
+// are independent of the SMs), so the call is bound by the larger of the two PCIe directions rather
+// than by their sum plus the compute.
 #include "pss_common.cuh"
+
+#define PIPE_CHUNK_BLOCKS 256     // 256 x 32768 complex64 = 64 MiB per host->device copy
+
+struct PipeStreams {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t in_ready[2] = {nullptr, nullptr};     // H2D of slot s finished
+    cudaEvent_t in_free[2] = {nullptr, nullptr};      // kernels reading slot s finished
+    cudaEvent_t done = nullptr;                       // kernels of the chunk finished
+    cudaEvent_t db_free = nullptr;                    // D2H of the db scratch finished
+};
+static PipeStreams g_pipe[16];
+
+static int pipe_streams(pss_ctx* ctx, PipeStreams** out) {
+    PipeStreams& p = g_pipe[ctx->device & 15];
+    if (!p.h2d) {
+        PSS_CUDA(ctx, cudaStreamCreateWithFlags(&p.h2d, cudaStreamNonBlocking));
+        PSS_CUDA(ctx, cudaStreamCreateWithFlags(&p.d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            PSS_CUDA(ctx, cudaEventCreateWithFlags(&p.in_ready[i], cudaEventDisableTiming));
+            PSS_CUDA(ctx, cudaEventCreateWithFlags(&p.in_free[i], cudaEventDisableTiming));
+        }
+        PSS_CUDA(ctx, cudaEventCreateWithFlags(&p.done, cudaEventDisableTiming));
+        PSS_CUDA(ctx, cudaEventCreateWithFlags(&p.db_free, cudaEventDisableTiming));
+    }
+    *out = &p;
+    return PSS_OK;
+}
 
 extern "C" int pss_pipeline_c64(pss_ctx* ctx, const float* iq_host, int64_t n_blocks, const pss_pipeline_io* io) {
     if (!ctx || !iq_host || !io || n_blocks < 0) return PSS_ERR_ARG;
@@ -12,11 +44,16 @@ extern "C" int pss_pipeline_c64(pss_ctx* ctx, const float* iq_host, int64_t n_bl
     const size_t n_bins = (size_t)io->N_fft - 4;
     const int out_len = io->plan ? pss_demod_plan_out_len(io->plan) : 0;
     const int ch = io->plan ? pss_demod_plan_channels(io->plan) : 0;
+    int64_t chunk = PIPE_CHUNK_BLOCKS;
+    if ((size_t)chunk * io->N_block * 8 > (256u << 20)) chunk = (256 << 20) / ((int64_t)io->N_block * 8);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_blocks) chunk = n_blocks;
+    const size_t blk_in = (size_t)io->N_block * 8;
     const size_t sz[7] = {
-        (size_t)n_blocks * io->N_block * 8,                 // 0 iq
-        (size_t)n_frames * n_bins * 4,                      // 1 db
-        (size_t)n_frames * io->W * 4,                       // 2 cols
-        (size_t)n_frames * 16,                              // 3 stats
+        2 * (size_t)chunk * blk_in,                         // 0 iq, two slots
+        (size_t)chunk * fpb * n_bins * 4,                   // 1 db of one chunk
+        (size_t)n_frames * io->W * 4,                       // 2 cols, whole batch (display history)
+        (size_t)n_frames * 16,                              // 3 stats, whole batch
         (size_t)n_blocks * io->rows_max * io->W * 4,        // 4 norm
         (size_t)n_blocks * 8,                               // 5 minmax
         (size_t)n_blocks * out_len * ch * 4 + 16,           // 6 audio
@@ -24,29 +61,76 @@ extern "C" int pss_pipeline_c64(pss_ctx* ctx, const float* iq_host, int64_t n_bl
     int rc;
     for (int i = 0; i < 7; ++i)
         if ((rc = pss_reserve(ctx, &ctx->p_buf[i], &ctx->p_bytes[i], sz[i]))) return rc;
+    PipeStreams* ps;
+    if ((rc = pipe_streams(ctx, &ps))) return rc;
     cudaStream_t st = ctx->stream;
-    PSS_CUDA(ctx, cudaMemcpyAsync(ctx->p_buf[0], iq_host, sz[0], cudaMemcpyHostToDevice, st));
-    pss_psd_out po;
-    po.db = (float*)ctx->p_buf[1];
-    po.cols = (float*)ctx->p_buf[2];
-    po.W = io->W;
-    po.stats = (float*)ctx->p_buf[3];
-    if ((rc = pss_psd_c64_dev(ctx, (const float*)ctx->p_buf[0], io->N_fft, n_frames, PSS_WINDOW_HAMMING,
-                              PSS_EPI_SMOOTH_CLAMP, PSS_PREC_FP64, &po)))
-        return rc;
-    if ((rc = pss_display_render_dev(ctx, po.cols, po.stats, io->W, n_frames, io->rows_max, fpb - 1, fpb, n_blocks, 0,
-                                     (float*)ctx->p_buf[4], (float*)ctx->p_buf[5])))
-        return rc;
-    if (io->plan)
-        if ((rc = pss_demod_c64_dev(ctx, io->plan, (const float*)ctx->p_buf[0], n_blocks, (float*)ctx->p_buf[6])))
+    char* d_iq = (char*)ctx->p_buf[0];
+    float* d_db = (float*)ctx->p_buf[1];
+    float* d_cols = (float*)ctx->p_buf[2];
+    float* d_stats = (float*)ctx->p_buf[3];
+    float* d_norm = (float*)ctx->p_buf[4];
+    float* d_mm = (float*)ctx->p_buf[5];
+    float* d_audio = (float*)ctx->p_buf[6];
+    // order the side streams after whatever the caller queued on the context stream
+    PSS_CUDA(ctx, cudaEventRecord(ps->done, st));
+    PSS_CUDA(ctx, cudaStreamWaitEvent(ps->h2d, ps->done, 0));
+    PSS_CUDA(ctx, cudaStreamWaitEvent(ps->d2h, ps->done, 0));
+    int slot = 0;
+    bool slot_used[2] = {false, false};
+    bool db_copy_pending = false;
+    for (int64_t b0 = 0; b0 < n_blocks; b0 += chunk, slot ^= 1) {
+        const int64_t nb = n_blocks - b0 < chunk ? n_blocks - b0 : chunk;
+        const int64_t f0 = b0 * fpb, nf = nb * fpb;
+        float* iq_slot = (float*)(d_iq + (size_t)slot * chunk * blk_in);
+        if (slot_used[slot]) PSS_CUDA(ctx, cudaStreamWaitEvent(ps->h2d, ps->in_free[slot], 0));
+        PSS_CUDA(ctx, cudaMemcpyAsync(iq_slot, (const char*)iq_host + (size_t)b0 * blk_in, (size_t)nb * blk_in,
+                                      cudaMemcpyHostToDevice, ps->h2d));
+        PSS_CUDA(ctx, cudaEventRecord(ps->in_ready[slot], ps->h2d));
+        slot_used[slot] = true;
+        PSS_CUDA(ctx, cudaStreamWaitEvent(st, ps->in_ready[slot], 0));
+        if (db_copy_pending) PSS_CUDA(ctx, cudaStreamWaitEvent(st, ps->db_free, 0));
+        pss_psd_out po;
+        po.db = d_db;
+        po.cols = d_cols + f0 * io->W;
+        po.W = io->W;
+        po.stats = d_stats + f0 * 4;
+        if ((rc = pss_psd_c64_dev(ctx, iq_slot, io->N_fft, nf, PSS_WINDOW_HAMMING, PSS_EPI_SMOOTH_CLAMP,
+                                  PSS_PREC_FP64, &po)))
             return rc;
-    if (io->db) PSS_CUDA(ctx, cudaMemcpyAsync(io->db, ctx->p_buf[1], sz[1], cudaMemcpyDeviceToHost, st));
-    if (io->cols) PSS_CUDA(ctx, cudaMemcpyAsync(io->cols, ctx->p_buf[2], sz[2], cudaMemcpyDeviceToHost, st));
-    if (io->stats) PSS_CUDA(ctx, cudaMemcpyAsync(io->stats, ctx->p_buf[3], sz[3], cudaMemcpyDeviceToHost, st));
-    if (io->norm) PSS_CUDA(ctx, cudaMemcpyAsync(io->norm, ctx->p_buf[4], sz[4], cudaMemcpyDeviceToHost, st));
-    if (io->minmax) PSS_CUDA(ctx, cudaMemcpyAsync(io->minmax, ctx->p_buf[5], sz[5], cudaMemcpyDeviceToHost, st));
-    if (io->audio && io->plan)
-        PSS_CUDA(ctx, cudaMemcpyAsync(io->audio, ctx->p_buf[6], sz[6] - 16, cudaMemcpyDeviceToHost, st));
+        // history of a block reaches back into earlier chunks: cols/stats are whole-batch arrays
+        if ((rc = pss_display_render_dev(ctx, d_cols, d_stats, io->W, f0 + nf, io->rows_max, f0 + fpb - 1, fpb, nb, 0,
+                                         d_norm + (size_t)b0 * io->rows_max * io->W, d_mm + b0 * 2)))
+            return rc;
+        if (io->plan)
+            if ((rc = pss_demod_c64_dev(ctx, io->plan, iq_slot, nb, d_audio + (size_t)b0 * out_len * ch))) return rc;
+        PSS_CUDA(ctx, cudaEventRecord(ps->in_free[slot], st));
+        PSS_CUDA(ctx, cudaEventRecord(ps->done, st));
+        // results of this chunk go home while the next chunk computes
+        PSS_CUDA(ctx, cudaStreamWaitEvent(ps->d2h, ps->done, 0));
+        if (io->db) {
+            PSS_CUDA(ctx, cudaMemcpyAsync(io->db + (size_t)f0 * n_bins, d_db, (size_t)nf * n_bins * 4,
+                                          cudaMemcpyDeviceToHost, ps->d2h));
+            PSS_CUDA(ctx, cudaEventRecord(ps->db_free, ps->d2h));
+            db_copy_pending = true;
+        }
+        if (io->cols)
+            PSS_CUDA(ctx, cudaMemcpyAsync(io->cols + (size_t)f0 * io->W, d_cols + f0 * io->W, (size_t)nf * io->W * 4,
+                                          cudaMemcpyDeviceToHost, ps->d2h));
+        if (io->stats)
+            PSS_CUDA(ctx, cudaMemcpyAsync(io->stats + (size_t)f0 * 4, d_stats + f0 * 4, (size_t)nf * 16,
+                                          cudaMemcpyDeviceToHost, ps->d2h));
+        if (io->norm)
+            PSS_CUDA(ctx, cudaMemcpyAsync(io->norm + (size_t)b0 * io->rows_max * io->W,
+                                          d_norm + (size_t)b0 * io->rows_max * io->W,
+                                          (size_t)nb * io->rows_max * io->W * 4, cudaMemcpyDeviceToHost, ps->d2h));
+        if (io->minmax)
+            PSS_CUDA(ctx, cudaMemcpyAsync(io->minmax + b0 * 2, d_mm + b0 * 2, (size_t)nb * 8, cudaMemcpyDeviceToHost,
+                                          ps->d2h));
+        if (io->audio && io->plan)
+            PSS_CUDA(ctx, cudaMemcpyAsync(io->audio + (size_t)b0 * out_len * ch, d_audio + (size_t)b0 * out_len * ch,
+                                          (size_t)nb * out_len * ch * 4, cudaMemcpyDeviceToHost, ps->d2h));
+    }
+    PSS_CUDA(ctx, cudaStreamSynchronize(ps->d2h));
     PSS_CUDA(ctx, cudaStreamSynchronize(st));
     return PSS_OK;
 }

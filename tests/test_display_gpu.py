@@ -57,3 +57,22 @@ def test_display_strided_renders(ctx):
     full, _ = ctx.display_render(res["cols"], res["stats"], rows_max=30)
     some, _ = ctx.display_render(res["cols"], res["stats"], rows_max=30, first=3, step=8, n_renders=3)
     np.testing.assert_array_equal(some, full[[3, 11, 19]])
+
+
+def test_pipeline_matches_separate_calls_across_chunks(ctx):
+    """pss_pipeline_c64 (chunked, overlapped copies) == the individual host-pointer calls, bitwise,
+    with more blocks than one copy chunk so the waterfall history crosses chunk boundaries."""
+    n_block, n_fft, W = 4096, 1024, 64
+    base = np.stack([synth.make("wbfm", n_block, seed=s, fs=1.024e6) for s in range(12)])
+    blocks = np.ascontiguousarray(np.tile(base, (50, 1))[:590])            # 590 blocks > 2 chunks of 256
+    out = ctx.pipeline(blocks, 1.024e6, "NFM", n_fft=n_fft, W=W, rows_max=30, want_db=True)
+    frames = blocks.reshape(-1, n_fft)
+    sep = ctx.psd(frames, epilogue=True, W=W, want_stats=True)
+    np.testing.assert_array_equal(out["db"], sep["db"])
+    np.testing.assert_array_equal(out["cols"], sep["cols"])
+    np.testing.assert_array_equal(out["stats"], sep["stats"])
+    fpb = n_block // n_fft
+    norm, mm = ctx.display_render(sep["cols"], sep["stats"], rows_max=30, first=fpb - 1, step=fpb, n_renders=len(blocks))
+    np.testing.assert_array_equal(out["norm"], norm)
+    np.testing.assert_array_equal(out["minmax"], mm)
+    np.testing.assert_array_equal(out["audio"], ctx.demod(blocks, 1.024e6, "NFM"))
