@@ -75,7 +75,9 @@ __device__ __forceinline__ float2 iq_apply(const float2 s, const IqCorr k) {
 __device__ __forceinline__ float fast_atan2f(const float im, const float re) {
     const float ax = fabsf(re), ay = fabsf(im);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    float t = __fdividef(mn, mx);
+    float rc;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(mx));      // 1 MUFU; t is within 1.5 ulp
+    float t = mn * rc;
     t = mx == 0.f ? 0.f : t;
     const float z = t * t;
     float p = 2.456712816e-03f;
@@ -121,24 +123,32 @@ __device__ __forceinline__ float discriminator(const float2* __restrict__ x, con
 //               registers;
 //   tile_store: IQ-correct (WFM), take the neighbour from the previous lane, discriminate, store the
 //               31 outputs of the iteration.  Each sample is loaded and corrected once.
-template <int PF>
+// EDGE_CHECK = false is the interior fast path: every sample index of the tile is inside the block,
+// so the loads and stores carry no range predicates.
+template <int PF, bool EDGE_CHECK>
 __device__ __forceinline__ void tile_load(float2 (&pf)[PF], const float2* __restrict__ x, const int g0,
                                           const int n_wi, const int N, const int warp, const int lane) {
+    const float2* xp = x + g0 + 31 * warp + lane;
 #pragma unroll
     for (int it = 0; it < PF; ++it) {
         const int wi = warp + it * (DEMOD_THREADS / 32);
-        const int gi = g0 + 31 * wi + lane;
+        bool ok = wi < n_wi;
+        if (EDGE_CHECK) {
+            const int gi = g0 + 31 * wi + lane;
+            ok = ok && gi >= 0 && gi < N;
+        }
         pf[it] = make_float2(0.f, 0.f);
-        if (wi < n_wi && gi >= 0 && gi < N) pf[it] = __ldg(x + gi);
+        if (ok) pf[it] = __ldg(xp + it * (31 * (DEMOD_THREADS / 32)));
     }
 }
 
-template <bool WFM, int PF>
+template <bool WFM, int PF, bool EDGE_CHECK>
 __device__ __forceinline__ void tile_store(float* __restrict__ buf, const float2 (&pf)[PF],
                                            const float2* __restrict__ x, const int g0, const int E,
                                            const int n_wi, const int N, const IqCorr k, const float scale,
                                            const int warp, const int lane) {
     const int L = N - 1;
+    float* bp = buf + 31 * warp + lane - 1;
 #pragma unroll
     for (int it = 0; it < PF; ++it) {
         const int wi = warp + it * (DEMOD_THREADS / 32);
@@ -147,11 +157,13 @@ __device__ __forceinline__ void tile_store(float* __restrict__ buf, const float2
         float2 prev;
         prev.x = __shfl_up_sync(0xffffffffu, cur.x, 1);
         prev.y = __shfl_up_sync(0xffffffffu, cur.y, 1);
-        const int e = 31 * wi + lane - 1;
-        const int g = g0 + e;
         float d = disc_core<WFM>(cur, prev, scale);
-        if (g < 0 || g >= L) d = 0.f;
-        if (wi < n_wi && lane > 0 && e < E) buf[e] = d;
+        const int e = 31 * wi + lane - 1;
+        if (EDGE_CHECK) {
+            const int g = g0 + e;
+            if (g < 0 || g >= L) d = 0.f;
+        }
+        if (wi < n_wi && lane > 0 && e < E) bp[it * (31 * (DEMOD_THREADS / 32))] = d;
     }
     // tiles larger than PF iterations per warp (very large q): finish without the register prefetch
     for (int wi = warp + PF * (DEMOD_THREADS / 32); wi < n_wi; wi += DEMOD_THREADS / 32) {
@@ -176,17 +188,26 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, const double
                  : "d"(a), "d"(b));
 }
 
-// One row of y = A x with x spread over the S lanes of a group (4 independent partial sums keep the
-// dependent fp64 chain short).
+// One row of y = A x with x spread over the S lanes of a group.  The state is broadcast through a
+// per-group shared-memory line (one 8-byte store, S/2 16-byte broadcast loads) instead of 2*S
+// shuffles; `xb` is the group's double-buffered line [2][S], `ph` flips every call.  Four independent
+// partial sums keep the dependent fp64 chain short.
 template <int S>
-__device__ __forceinline__ double matvec_row(const double (&a)[S], const double x, const int lane_base) {
+__device__ __forceinline__ double matvec_row(const double (&a)[S], const double x, double* xb, int& ph,
+                                             const int r) {
+    double* line = xb + ph * S;
+    ph ^= 1;
+    line[r] = x;
+    __syncwarp();
+    const double2* l2 = reinterpret_cast<const double2*>(line);
     double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
 #pragma unroll
     for (int c = 0; c < S; c += 4) {
-        p0 = fma(a[c], __shfl_sync(0xffffffffu, x, lane_base + c), p0);
-        p1 = fma(a[c + 1], __shfl_sync(0xffffffffu, x, lane_base + c + 1), p1);
-        p2 = fma(a[c + 2], __shfl_sync(0xffffffffu, x, lane_base + c + 2), p2);
-        p3 = fma(a[c + 3], __shfl_sync(0xffffffffu, x, lane_base + c + 3), p3);
+        const double2 u = l2[c / 2], v = l2[c / 2 + 1];
+        p0 = fma(a[c], u.x, p0);
+        p1 = fma(a[c + 1], u.y, p1);
+        p2 = fma(a[c + 2], v.x, p2);
+        p3 = fma(a[c + 3], v.y, p3);
     }
     return (p0 + p1) + (p2 + p3);
 }
@@ -196,10 +217,11 @@ __device__ __forceinline__ double matvec_row(const double (&a)[S], const double 
 template <int S>
 __device__ void blocked_scan(double* U, const int rows, const int foff, const int n, const bool fwd,
                              const double* __restrict__ A, const double* __restrict__ APow, const int B,
-                             const double* x0, double* XS, const int tid) {
+                             const double* x0, double* XS, double* XB, const int tid) {
     const int r = tid % S, grp = tid / S;
-    const int lane_base = (tid & 31) & ~(S - 1);
     const int n_units = (n + B - 1) / B;
+    double* xb = XB + (size_t)grp * 2 * S;      // this group's broadcast line (double-buffered)
+    int ph = 0;
     double a[S];
 #pragma unroll
     for (int c = 0; c < S; ++c) a[c] = A[r * S + c];
@@ -212,7 +234,7 @@ __device__ void blocked_scan(double* U, const int rows, const int foff, const in
             const bool act = grp < n_units && i < n;
             const int slot = fwd ? 1 + i : n - i;
             const double u = act ? U[slot * rows + foff + r] : 0.0;
-            x = u + matvec_row<S>(a, x, lane_base);
+            x = u + matvec_row<S>(a, x, xb, ph, r);
             if (act) U[slot * rows + foff + r] = x;
         }
     }
@@ -229,7 +251,7 @@ __device__ void blocked_scan(double* U, const int rows, const int foff, const in
             const bool more = ilast < n;          // a full block follows
             const int slot = fwd ? 1 + ilast : n - ilast;
             const double u = (more && grp == 0) ? U[slot * rows + foff + r] : 0.0;
-            X = u + matvec_row<S>(ap, X, lane_base);
+            X = u + matvec_row<S>(ap, X, xb, ph, r);
         }
     }
     __syncthreads();
@@ -240,7 +262,7 @@ __device__ void blocked_scan(double* U, const int rows, const int foff, const in
             const int i = i0 + s;
             const bool act = grp < n_units && i < n;
             const int slot = fwd ? 1 + i : n - i;
-            z = matvec_row<S>(a, z, lane_base);
+            z = matvec_row<S>(a, z, xb, ph, r);
             if (act) U[slot * rows + foff + r] += z;
         }
     }
@@ -257,7 +279,8 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
     float* tile = reinterpret_cast<float*>(smem + D.off_tile);
     double* misc = reinterpret_cast<double*>(smem + D.off_misc);
     double* XS = misc;                 // [32][16]
-    double* dh = misc + 512;           // [28] head discriminator samples
+    double* XB = misc + 512;           // [groups][2][S] scan broadcast lines
+    double* dh = misc + 1024;          // [28] head discriminator samples
     double* red = dh + 32;             // [32] reduction scratch
     double* tres = red + 32;           // [SB + m_tail] tail result (<= 64)
     double* yout = tres + 64;          // [n_out]
@@ -340,8 +363,8 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
         constexpr int PF = T == 32 ? 16 : 8;
         float2 pf[PF];
         if (n_tiles > 0) {
-            tile_load<PF>(pf, x, 1 - lead, n_wi, D.N, warp, lane);
-            tile_store<WFM, PF>(tile, pf, x, 1 - lead, E, n_wi, D.N, kc, D.scale, warp, lane);
+            tile_load<PF, true>(pf, x, 1 - lead, n_wi, D.N, warp, lane);
+            tile_store<WFM, PF, true>(tile, pf, x, 1 - lead, E, n_wi, D.N, kc, D.scale, warp, lane);
         }
         __syncthreads();
         if (tid <= SF) {
@@ -358,7 +381,12 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
             const float* cur = tile + (NBUF == 2 ? (tl & 1) * D.tile_floats : 0);
             const int g_next = (j0 + T - 1) * q + 1 - lead;
             const bool more = tl + 1 < n_tiles;
-            if (more) tile_load<PF>(pf, x, g_next, n_wi, D.N, warp, lane);
+            // interior tile: every IQ index g_next .. g_next + 31*n_wi lies inside the block
+            const bool interior = g_next >= 0 && g_next + 31 * n_wi + 1 < D.N;
+            if (more) {
+                if (interior) tile_load<PF, false>(pf, x, g_next, n_wi, D.N, warp, lane);
+                else tile_load<PF, true>(pf, x, g_next, n_wi, D.N, warp, lane);
+            }
             {
                 // work split over the 8 warps: a unit = (m-tile of 8 chunks, n-tile of 8 table rows)
                 // over the whole window.  MT*NT is 8 or 16 -> whole units per warp, plain stores.
@@ -407,14 +435,16 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
                 }
             }
             if (NBUF == 1) __syncthreads();
-            if (more)
-                tile_store<WFM, PF>(tile + (NBUF == 2 ? ((tl + 1) & 1) * D.tile_floats : 0), pf, x, g_next, E, n_wi,
-                                    D.N, kc, D.scale, warp, lane);
+            if (more) {
+                float* nxt = tile + (NBUF == 2 ? ((tl + 1) & 1) * D.tile_floats : 0);
+                if (interior) tile_store<WFM, PF, false>(nxt, pf, x, g_next, E, n_wi, D.N, kc, D.scale, warp, lane);
+                else tile_store<WFM, PF, true>(nxt, pf, x, g_next, E, n_wi, D.N, kc, D.scale, warp, lane);
+            }
             __syncthreads();
         }
 
         // ---- forward state scan: slot j .F becomes s_{j+1} (state after chunk j)
-        blocked_scan<SF>(U, ROWS, 0, n_body, true, D.AF, D.AFB, D.Bf, U, XS, tid);
+        blocked_scan<SF>(U, ROWS, 0, n_body, true, D.AF, D.AFB, D.Bf, U, XS, XB, tid);
 
         // ---- tail block: reversed-pass state entering chunk n_body, and the last m_tail outputs
         for (int i = tid; i < D.tail_len; i += DEMOD_THREADS)
@@ -456,7 +486,7 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
         __syncthreads();
 
         // ---- backward state scan: slot j .Bk becomes t_j (reversed-pass state after chunk j)
-        blocked_scan<SB>(U, ROWS, SF, n_body, false, D.AB, D.ABB, D.Bb, tres, XS, tid);
+        blocked_scan<SB>(U, ROWS, SF, n_body, false, D.AB, D.ABB, D.Bb, tres, XS, XB, tid);
 
         // ---- outputs
         for (int j = tid; j <= n_body; j += DEMOD_THREADS) {
@@ -543,7 +573,7 @@ static int create_decim(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
     // shared-memory layout: tile(s) + misc always; table and state slots when they fit in 113 KB.
     // Preference: 32-chunk double-buffered tiles, then smaller / single-buffered ones.
     const size_t budget = 113 * 1024;
-    const size_t misc_b = ((size_t)(512 + 32 + 32 + 64 + D.n_out) * 8 + 15) & ~(size_t)15;
+    const size_t misc_b = ((size_t)(512 + 512 + 32 + 32 + 64 + D.n_out) * 8 + 15) & ~(size_t)15;
     const size_t tab_b = frag.size() * 8;
     D.U_bytes = (((size_t)(D.n_body + 2) * D.rows * 8) + 15) & ~(size_t)15;
     const int cand[4][2] = {{32, 2}, {16, 2}, {32, 1}, {16, 1}};
@@ -707,7 +737,8 @@ demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
     const int n_chunks = (N + C - 1) / C;                 // <= FRAME_THREADS
     double* US = reinterpret_cast<double*>(smem);         // [(n_chunks + 2)][16] scan slots
     double* XS = US + (size_t)(FRAME_THREADS + 2) * 16;   // [32][16]
-    double* redd = XS + 512;                              // [32]
+    double* XB = XS + 512;                                // [32 groups][2][16] scan broadcast lines
+    double* redd = XB + 1024;                             // [32]
     float* row = reinterpret_cast<float*>(redd + 32);     // [N + N/C] skewed: idx + idx / C
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double c[NS][5];
@@ -761,7 +792,7 @@ demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
         }
         __syncthreads();
         // true state after every chunk: x_{c+1} = AC x_c + u_c, x_0 = 0 (slot 0 stays zero)
-        blocked_scan<16>(US, 16, 0, n_chunks, true, D.AC, D.ACB, D.B, US, XS, tid);
+        blocked_scan<16>(US, 16, 0, n_chunks, true, D.AC, D.ACB, D.B, US, XS, XB, tid);
         // pass B: re-run from the true initial state (slot tid = state after chunk tid-1), in place
         float mx = 0.f;
         if (tid < n_chunks) {
@@ -914,7 +945,7 @@ static int create_frame(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
     if ((rc = upload(ctx, pl, d->sos, (size_t)ns * 6 * 8, &p))) return rc; F.sos = (const double*)p;
     if ((rc = upload(ctx, pl, AC.data(), 256 * 8, &p))) return rc; F.AC = (const double*)p;
     if ((rc = upload(ctx, pl, ACB.data(), 256 * 8, &p))) return rc; F.ACB = (const double*)p;
-    F.smem_bytes = ((size_t)(FRAME_THREADS + 2) * 16 * 8 + 512 * 8 + 32 * 8 + ((size_t)d->N + d->N / F.C + 8) * 4 + 15) & ~(size_t)15;
+    F.smem_bytes = ((size_t)(FRAME_THREADS + 2) * 16 * 8 + 512 * 8 + 1024 * 8 + 32 * 8 + ((size_t)d->N + d->N / F.C + 8) * 4 + 15) & ~(size_t)15;
     if (F.smem_bytes > 220 * 1024) return PSS_ERR_UNSUPPORTED;
     return PSS_OK;
 }
