@@ -62,15 +62,16 @@ def make_blocks_numpy(n_blocks, seed):
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
+_CPU_BLOCKS = None      # set before the fork pool is created so workers inherit the data without pickling
+
+
 def _oracle_block_worker(args):
     """Process a contiguous range of blocks exactly as the reference's main loop would."""
-    blocks, mode = args
-    os.environ["OMP_NUM_THREADS"] = "1"
+    lo, hi, mode = args
     from oracle import ref_dsp as O
     hist = []
     acc = 0.0
-    t0 = time.perf_counter()
-    for blk in blocks:
+    for blk in _CPU_BLOCKS[lo:hi]:
         audio = O.demod(blk, FS, mode)
         acc += float(audio[0, 0])
         for f in range(N_BLOCK // N_FFT):
@@ -82,25 +83,36 @@ def _oracle_block_worker(args):
                     hist.pop(0)
         norm, _, _, _ = O.waterfall_accumulate(hist, row, W_COLS, ROWS_MAX)
         acc += float(norm[0, 0]) + pk + av
-    return time.perf_counter() - t0, acc
+    return acc
 
 
-def cpu_reference(blocks_c64, mode, cores=None):
-    """Oracle port over all host cores (disjoint block ranges per process). Returns (Msamples/s, info)."""
-    import multiprocessing as mp
-    cores = cores or os.cpu_count() or 1
-    nb = len(blocks_c64)
-    cores = max(1, min(cores, nb))
-    parts = [blocks_c64[i * nb // cores:(i + 1) * nb // cores] for i in range(cores)]
-    ctxm = mp.get_context("fork")
-    with ctxm.Pool(cores) as pool:
-        pool.map(_oracle_block_worker, [(p[:1], mode) for p in parts])       # warm the workers / caches
+class CpuReference:
+    """The reference's CPU path (oracle port: the same numpy/scipy calls) over all host cores: one
+    forked worker per core, disjoint contiguous block ranges, single-threaded BLAS/OpenMP per worker."""
+
+    def __init__(self, blocks_c64, mode, cores=None):
+        global _CPU_BLOCKS
+        import multiprocessing as mp
+        os.environ["OMP_NUM_THREADS"] = "1"
+        os.environ["OPENBLAS_NUM_THREADS"] = "1"
+        os.environ["MKL_NUM_THREADS"] = "1"
+        _CPU_BLOCKS = blocks_c64
+        self.mode = mode
+        self.nb = len(blocks_c64)
+        self.cores = max(1, min(cores or os.cpu_count() or 1, self.nb))
+        self.pool = mp.get_context("fork").Pool(self.cores)
+        self.parts = [(i * self.nb // self.cores, (i + 1) * self.nb // self.cores, mode) for i in range(self.cores)]
+        self.pool.map(_oracle_block_worker, [(lo, min(hi, lo + 1), mode) for lo, hi, _ in self.parts])   # warm
+
+    def step(self):
+        """One pass over the sample; returns wall seconds."""
         t0 = time.perf_counter()
-        res = pool.map(_oracle_block_worker, [(p, mode) for p in parts])
-        wall = time.perf_counter() - t0
-    busy = max(r[0] for r in res)
-    samples = nb * N_BLOCK
-    return samples / busy / 1e6, dict(cores=cores, blocks=nb, wall_s=wall, busy_s=busy)
+        self.pool.map(_oracle_block_worker, self.parts)
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -175,18 +187,16 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cores = os.cpu_count() or 1
         args.cpu_blocks = min(args.cpu_blocks, 512)        # keeps K steps within a few minutes on any host
         blocks = make_blocks_numpy(args.cpu_blocks, seed=0)
-        for _ in range(max(args.warmup, 0) and 1):
-            cpu_reference(blocks[:cores], args.mode)
-        vals, info = [], None
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            v, info = cpu_reference(blocks, args.mode)
-            vals.append(v)
-        ms = (time.perf_counter() - t0) / args.steps * 1e3
-        v = float(np.mean(vals))
+        ref = CpuReference(blocks, args.mode)
+        for _ in range(args.warmup):
+            ref.step()
+        walls = [ref.step() for _ in range(args.steps)]
+        ref.close()
+        ms = float(np.mean(walls)) * 1e3
+        v = args.cpu_blocks * N_BLOCK / (ms * 1e-3) / 1e6
+        info = {"cores": ref.cores}
         sample = f"{args.cpu_blocks} blocks x {N_BLOCK} samples per step, numpy/scipy oracle port, fork pool"
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
@@ -357,10 +367,12 @@ def main():
 
     if rank == 0 and not args.no_cpu:
         hb = np.ascontiguousarray(host_iq[:args.cpu_blocks])
-        v, info = cpu_reference(hb, args.mode)
-        cpu_base = {"value": v, "unit": "Msamples/s", "cores": info["cores"], "kind": "port",
+        ref = CpuReference(hb, args.mode)
+        wall = ref.step()
+        ref.close()
+        cpu_base = {"value": len(hb) * N_BLOCK / wall / 1e6, "unit": "Msamples/s", "cores": ref.cores, "kind": "port",
                     "sample": f"first {len(hb)} blocks x {N_BLOCK} samples of this run's input, numpy/scipy oracle "
-                              f"port, one fork-pool process per core (busy {info['busy_s']:.1f} s)"}
+                              f"port, one forked worker per core, wall {wall:.2f} s = {wall * ref.cores:.0f} core-s"}
 
     if rank == 0:
         print(json.dumps({
