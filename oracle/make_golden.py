@@ -111,11 +111,14 @@ def main():
     assert "mask" in bw_src and "bandwidth" in bw_src, bw_src
 
     epi = {}
-    for kind, n in (("noise", 1024), ("tone40", 4096), ("wbfm", 4096), ("tone60", 8192)):
+    for kind, n in (("noise", 1024), ("tone40", 4096), ("wbfm", 4096), ("tone60", 8192), ("halfband", 4096),
+                    ("halfband", 1024)):
         x = synth.make(kind, n, seed=5)
         env = {"np": np, "freq_data": ref.compute_fft(x)}
         exec(epi_src, env)
         epi[f"{kind}_{n}"] = env["freq_data"]
+        if kind == "halfband":      # this case exists to pin the clamp: make sure it fires
+            assert np.sum(env["freq_data"] == env["freq_data"].min()) > n // 10
         epi[f"{kind}_{n}_in"] = np.array(digest(x))
     np.savez_compressed(os.path.join(OUT, "epilogue.npz"), **epi)
 

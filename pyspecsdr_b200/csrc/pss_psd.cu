@@ -87,7 +87,11 @@ __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<
 // LOG2N1 > 0: this launch is the second stage of a length N*2^LOG2N1 transform (four-step FFT): frame
 // index = big_frame * N1 + k1, input = column-transformed, twiddled fp64 rows, output bin = k1 + N1*k2.
 template <int LOG2N, typename T, int EPI, int LOG2N1 = 0>
-__global__ void __launch_bounds__(PsdCfg<LOG2N, T>::THREADS, PsdCfg<LOG2N, T>::MINB)
+// The smoothing/median epilogue is latency-bound (barriers, shared-memory atomics), so that variant
+// is held to 80 registers for 3 CTAs/SM (measured +14 %; ptxas fits the radix-16 passes without
+// spills); the raw variant is fp64-pipe-bound and is faster at 2 CTAs/SM with ~110 registers.
+__global__ void __launch_bounds__(PsdCfg<LOG2N, T>::THREADS,
+                                  (EPI == EPI_SMOOTH && PsdCfg<LOG2N, T>::MINB == 2) ? 3 : PsdCfg<LOG2N, T>::MINB)
 psd_kernel(const PsdParams p) {
     using C = PsdCfg<LOG2N, T>;
     constexpr int N = C::N, TPF = C::TPF, NP = C::NP;

@@ -12,7 +12,7 @@ from __future__ import annotations
 import numpy as np
 
 __all__ = [
-    "noise", "tone_noise", "wbfm", "am_tone", "ssb_two_tone", "scanner_frames",
+    "noise", "tone_noise", "wbfm", "am_tone", "ssb_two_tone", "scanner_frames", "halfband",
     "impulse", "KINDS", "make",
 ]
 
@@ -83,6 +83,17 @@ def scanner_frames(n_steps: int, n: int, seed: int = 0) -> np.ndarray:
     return out
 
 
+def halfband(n: int, seed: int = 0, frac: float = 0.6, floor_db: float = -35.0) -> np.ndarray:
+    """Noise filling `frac` of the band at 0 dB and the rest `floor_db` lower: more than half of the
+    spectrum sits far above the remaining bins, so the main loop's median-10 dB clamp fires."""
+    rng = np.random.default_rng(seed)
+    spec = _cnoise(rng, n, 1.0) * np.sqrt(n)
+    k = np.arange(n)
+    lo = (k > frac * n)
+    spec[lo] *= 10.0 ** (floor_db / 20.0)
+    return np.fft.ifft(spec).astype(np.complex64)
+
+
 def impulse(n: int, pos: int = 0, amp: complex = 1.0 + 0.5j) -> np.ndarray:
     x = np.zeros(n, dtype=np.complex64)
     x[pos] = amp
@@ -96,6 +107,7 @@ KINDS = {
     "wbfm": wbfm,
     "am": am_tone,
     "ssb": ssb_two_tone,
+    "halfband": halfband,
 }
 
 

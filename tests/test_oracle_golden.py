@@ -43,7 +43,8 @@ def test_psd_batched_equals_rowwise():
     np.testing.assert_array_equal(O.psd_db(x), np.stack([O.psd_db(r) for r in x]))
 
 
-@pytest.mark.parametrize("kind,n", [("noise", 1024), ("tone40", 4096), ("wbfm", 4096), ("tone60", 8192)])
+@pytest.mark.parametrize("kind,n", [("noise", 1024), ("tone40", 4096), ("wbfm", 4096), ("tone60", 8192),
+                                    ("halfband", 4096), ("halfband", 1024)])
 def test_epilogue(golden, kind, n):
     g = golden("epilogue")
     x = synth.make(kind, n, seed=5)

@@ -53,7 +53,7 @@ def test_psd_ragged_batch_and_empty(ctx):
 
 
 @pytest.mark.parametrize("n", [512, 1024, 4096, 8192])
-@pytest.mark.parametrize("kind", ["noise", "tone40", "wbfm"])
+@pytest.mark.parametrize("kind", ["noise", "tone40", "wbfm", "halfband"])
 def test_psd_epilogue_vs_oracle(ctx, n, kind):
     x = frames(kind, n, 4, seed0=3)
     W = 193
@@ -71,10 +71,27 @@ def test_psd_epilogue_vs_oracle(ctx, n, kind):
 
 def test_psd_epilogue_golden(ctx, golden):
     g = golden("epilogue")
-    for kind, n in (("noise", 1024), ("tone40", 4096), ("wbfm", 4096), ("tone60", 8192)):
+    for kind, n in (("noise", 1024), ("tone40", 4096), ("wbfm", 4096), ("tone60", 8192), ("halfband", 4096),
+                    ("halfband", 1024)):
         x = synth.make(kind, n, seed=5)
         got = ctx.psd(x, epilogue=True)["db"][0]
         assert np.max(np.abs(got - g[f"{kind}_{n}"])) <= TOL_DB
+
+
+def test_psd_epilogue_clamp_fires_and_mixed_batch(ctx):
+    """Frames that need the exact median select (clamp fires) mixed with frames that take the fast
+    path, inside one CTA (4 frames of 1024 per CTA) and across CTAs."""
+    kinds = ["halfband", "noise", "tone40", "halfband", "noise", "halfband", "wbfm", "noise", "halfband"]
+    for n in (1024, 4096, 16384):
+        x = np.stack([synth.make(k, n, seed=40 + i) for i, k in enumerate(kinds)])
+        got = ctx.psd(x, epilogue=True, want_stats=True)
+        fired = 0
+        for f in range(len(x)):
+            want = O.psd_epilogue(O.psd_db(x[f]))
+            fired += int(np.sum(want == want.min()) > 10)
+            assert np.max(np.abs(got["db"][f] - want)) <= TOL_DB, (n, f, kinds[f])
+            assert abs(got["stats"][f][2] - want.min()) <= TOL_DB
+        assert fired >= 4
 
 
 def test_psd_epilogue_constant_row(ctx):
