@@ -98,6 +98,15 @@ int pss_scan_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_steps, int use_
 int pss_scan_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_steps, int use_abs,
                      float thr_db, float* peak_db, int32_t* count_above, float* db_rows);
 
+/* Replaces the numeric part of draw_spectrogram (pyspecsdr.py:418-452): noise floor = 20th percentile
+ * of the row (np.percentile, linear interpolation), display range [floor - 0.1*span, max + 0.05*span],
+ * clip to [0,1], ** 0.7, W-column np.interp resample.  db [n_frames][n_bins] (host), cols [n_frames][W],
+ * range [n_frames][2] = display_min, display_max (may be NULL).
+ * (draw_surface_plot :1575-1596 needs no kernel of its own: it is pss_display_render with rows_max = 1,
+ *  guard_zero_range = 1, followed by int(v * 20).) */
+int pss_spectrum_normalise(pss_ctx* ctx, const float* db, int n_bins, int64_t n_frames, int W, float* cols,
+                           float* range);
+
 /* ------------------------------------------------------------------ demodulation
  * Replaces demodulate_signal(samples, sample_rate, mode)  signal_processing.py:220-240 and the
  * per-mode chains demodulate_nfm :91-116, demodulate_wfm :119-176 (+ iq_correction :46-80),

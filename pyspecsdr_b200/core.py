@@ -300,3 +300,20 @@ class Context:
         out = np.empty(a.shape, np.int16)
         self._ck(lib.pss_audio_to_int16(self._h, a.ctypes.data, a.size, out.ctypes.data), "pss_audio_to_int16")
         return out
+
+    def spectrum_normalise(self, db_rows, W: int):
+        """draw_spectrogram's numeric part (pyspecsdr.py:418-452).  Returns (cols [F, W] in [0,1],
+        range [F, 2] = display_min, display_max)."""
+        d = np.ascontiguousarray(db_rows, dtype=np.float32)
+        fr = d[None, :] if d.ndim == 1 else d
+        cols = np.empty((len(fr), W), np.float32)
+        rng = np.empty((len(fr), 2), np.float32)
+        self._ck(lib.pss_spectrum_normalise(self._h, fr.ctypes.data, fr.shape[1], fr.shape[0], W, cols.ctypes.data,
+                                            rng.ctypes.data), "pss_spectrum_normalise")
+        return cols, rng
+
+    def surface_row(self, cols, stats):
+        """draw_surface_plot's numeric part (pyspecsdr.py:1575-1596) from a PSD row's W-column resample
+        and its min/max: magnitude = int(normalised * 20)."""
+        norm, mm = self.display_render(cols, stats, rows_max=1, guard_zero_range=True)
+        return (norm[:, 0].astype(np.float64) * 20).astype(np.int64), mm

@@ -119,3 +119,101 @@ __device__ __forceinline__ float db_from_power(double p) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(pf));
     return 3.01029995663981195f * l;
 }
+
+// Order-preserving float <-> unsigned key (total order: -inf < ... < -0 < +0 < ... < +inf < NaN).
+__device__ __forceinline__ unsigned f2key(float f) {
+    unsigned u = __float_as_uint(f);
+    return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float key2f(unsigned k) {
+    unsigned u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+    return __uint_as_float(u);
+}
+
+// Exact order statistics of a row streamed from global/L2 memory by one CTA of 512 threads:
+// returns the keys of the elements of (0-based) rank `rank` and rank+1 (rank+1 clamped to n-1).
+// 4 x 8-bit radix select on keys normalised to the occupied range, then one counting pass.
+// `hist` [256] and `us` [8] are shared scratch; all threads of the CTA must call it.
+__device__ __forceinline__ void row_select2_512(const float* __restrict__ row, const int n, const unsigned rank_in,
+                                                unsigned* hist, unsigned* us, unsigned& key_a, unsigned& key_b) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 8) us[tid] = (tid == 0 || tid == 5) ? 0xffffffffu : 0u;
+    __syncthreads();
+    unsigned kmin = 0xffffffffu, kmax = 0u;
+    for (int i = tid; i < n; i += 512) {
+        const unsigned k = f2key(row[i]);
+        kmin = min(kmin, k);
+        kmax = max(kmax, k);
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) {
+        atomicMin(&us[0], kmin);
+        atomicMax(&us[1], kmax);
+    }
+    __syncthreads();
+    kmin = us[0];
+    kmax = us[1];
+    const int common = min(__clz((int)(kmin ^ kmax)), 31);
+    unsigned rank = rank_in, prefix = 0u;
+    for (int ps = 0; ps < 4; ++ps) {
+        const int shift = 24 - 8 * ps;
+        if (tid < 256) hist[tid] = 0u;
+        __syncthreads();
+        for (int i = tid; i < n; i += 512) {
+            const unsigned k = (f2key(row[i]) - kmin) << common;
+            if (ps == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned c[8], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                c[q] = hist[8 * lane + q];
+                sum += c[q];
+            }
+            unsigned incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, incl > rank);
+            const int Ln = __ffs(hit) - 1;
+            if (lane == Ln) {
+                unsigned r = rank - (incl - sum);
+                int dg = 0;
+                bool found = false;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (!found) {
+                        if (r < c[q]) { dg = q; found = true; }
+                        else r -= c[q];
+                    }
+                }
+                us[2] = (unsigned)(8 * lane + dg);
+                us[3] = r;
+            }
+        }
+        __syncthreads();
+        prefix = (prefix << 8) | us[2];
+        rank = us[3];
+    }
+    unsigned cnt_le = 0, min_gt = 0xffffffffu;
+    for (int i = tid; i < n; i += 512) {
+        const unsigned k = (f2key(row[i]) - kmin) << common;
+        cnt_le += k <= prefix;
+        if (k > prefix) min_gt = min(min_gt, k);
+    }
+    cnt_le = __reduce_add_sync(0xffffffffu, cnt_le);
+    min_gt = __reduce_min_sync(0xffffffffu, min_gt);
+    if (lane == 0) {
+        atomicAdd(&us[4], cnt_le);
+        atomicMin(&us[5], min_gt);
+    }
+    __syncthreads();
+    key_a = (prefix >> common) + kmin;
+    const unsigned nb = (us[4] > rank_in + 1u || us[5] == 0xffffffffu) ? prefix : us[5];
+    key_b = (nb >> common) + kmin;
+    __syncthreads();
+}

@@ -38,6 +38,53 @@ display_render_kernel(const float* __restrict__ cols, const float* __restrict__ 
     }
 }
 
+// draw_spectrogram's numeric part (pyspecsdr.py:418-452): 20th-percentile noise floor (np.percentile,
+// linear interpolation between order statistics), display range, clip, ** 0.7, W-column resample.
+__global__ void __launch_bounds__(512)
+spectrum_normalise_kernel(const float* __restrict__ db, const int n, const long long n_frames, const int W,
+                          float* __restrict__ cols, float* __restrict__ range_out) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned us[8];
+    __shared__ float fmx[16];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
+        const float* row = db + f * n;
+        // noise floor: np.percentile(row, 20) = x[k] + frac * (x[k+1] - x[k]) on the sorted row
+        const double pos = 0.2 * (double)(n - 1);
+        const unsigned k = (unsigned)pos;
+        const double frac = pos - (double)k;
+        unsigned ka, kb;
+        row_select2_512(row, n, k, hist, us, ka, kb);
+        const double xa = key2f(ka), xb = key2f(kb);
+        const double floor_db = xa + frac * (xb - xa);
+        float mx = -INFINITY;
+        for (int i = tid; i < n; i += 512) mx = fmaxf(mx, row[i]);
+        mx = warp_max(mx);
+        if (lane == 0) fmx[warp] = mx;
+        __syncthreads();
+        mx = fmx[0];
+        for (int w = 1; w < 16; ++w) mx = fmaxf(mx, fmx[w]);
+        const double span = (double)mx - floor_db;                  // :425
+        const double dmin = floor_db - span * 0.1;                  // :426
+        const double dmax = (double)mx + span * 0.05;               // :427
+        if (tid == 0 && range_out) {
+            range_out[2 * f] = (float)dmin;
+            range_out[2 * f + 1] = (float)dmax;
+        }
+        const double inv = 1.0 / (dmax - dmin);
+        const double step = W > 1 ? (double)(n - 1) / (double)(W - 1) : 0.0;
+        for (int c = tid; c < W; c += 512) {
+            const double x = (c == W - 1 && W > 1) ? (double)(n - 1) : c * step;
+            const int j = min((int)x, n - 1);
+            const int j1 = min(j + 1, n - 1);
+            const double v0 = pow(fmin(fmax(((double)row[j] - dmin) * inv, 0.0), 1.0), 0.7);    // :442, :445
+            const double v1 = pow(fmin(fmax(((double)row[j1] - dmin) * inv, 0.0), 1.0), 0.7);
+            cols[f * W + c] = (float)((v1 - v0) * (x - (double)j) + v0);
+        }
+        __syncthreads();
+    }
+}
+
 void pss_display_release(pss_ctx*) {}
 
 extern "C" {
@@ -77,6 +124,28 @@ int pss_display_render(pss_ctx* ctx, const float* cols, const float* stats, int 
     if (rc) return rc;
     PSS_CUDA(ctx, cudaMemcpyAsync(norm, ctx->d_out, norm_b, cudaMemcpyDeviceToHost, ctx->stream));
     PSS_CUDA(ctx, cudaMemcpyAsync(minmax, ctx->d_aux2, mm_b, cudaMemcpyDeviceToHost, ctx->stream));
+    PSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PSS_OK;
+}
+
+
+int pss_spectrum_normalise(pss_ctx* ctx, const float* db, int n_bins, int64_t n_frames, int W, float* cols,
+                           float* range) {
+    if (!ctx || !db || !cols || n_bins < 2 || W < 1 || n_frames < 0) return PSS_ERR_ARG;
+    if (n_frames == 0) return PSS_OK;
+    PSS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t in_b = (size_t)n_frames * n_bins * 4, out_b = (size_t)n_frames * W * 4;
+    int rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_in, &ctx->d_in_bytes, in_b))) return rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_out, &ctx->d_out_bytes, out_b))) return rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_aux2, &ctx->d_aux2_bytes, (size_t)n_frames * 8))) return rc;
+    PSS_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, db, in_b, cudaMemcpyHostToDevice, ctx->stream));
+    const long long grid = n_frames < 4LL * ctx->sm_count ? n_frames : 4LL * ctx->sm_count;
+    spectrum_normalise_kernel<<<(unsigned)grid, 512, 0, ctx->stream>>>((const float*)ctx->d_in, n_bins, n_frames, W,
+                                                                      (float*)ctx->d_out, (float*)ctx->d_aux2);
+    PSS_LAUNCH_CHECK(ctx);
+    PSS_CUDA(ctx, cudaMemcpyAsync(cols, ctx->d_out, out_b, cudaMemcpyDeviceToHost, ctx->stream));
+    if (range) PSS_CUDA(ctx, cudaMemcpyAsync(range, ctx->d_aux2, (size_t)n_frames * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return PSS_OK;
 }

@@ -43,14 +43,6 @@ struct PsdCfg {
     static constexpr int NP = pss_num_passes(LOG2N);
 };
 
-__device__ __forceinline__ unsigned f2key(float f) {
-    unsigned u = __float_as_uint(f);
-    return u ^ ((unsigned)((int)u >> 31) | 0x80000000u);
-}
-__device__ __forceinline__ float key2f(unsigned k) {
-    unsigned u = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
-    return __uint_as_float(u);
-}
 
 // One Stockham pass P >= 1 (shared -> registers -> shared, or -> `out` on the last pass).
 template <int LOG2N, int P, typename T, typename OutF>

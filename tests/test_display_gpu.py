@@ -76,3 +76,32 @@ def test_pipeline_matches_separate_calls_across_chunks(ctx):
     np.testing.assert_array_equal(out["norm"], norm)
     np.testing.assert_array_equal(out["minmax"], mm)
     np.testing.assert_array_equal(out["audio"], ctx.demod(blocks, 1.024e6, "NFM"))
+
+
+def test_spectrum_normalise_vs_oracle(ctx):
+    """a7: 20th-percentile floor, clip, ** 0.7, resample (pyspecsdr.py:418-452)."""
+    x, ref_rows = make_rows(6, 4096)
+    W = 113
+    db = ctx.psd(x, epilogue=True)["db"]
+    cols, rng = ctx.spectrum_normalise(db, W)
+    for f, r in enumerate(ref_rows):
+        want, (dmin, dmax) = O.spectrum_normalise(r, W)
+        assert abs(rng[f, 0] - dmin) <= 2e-4 and abs(rng[f, 1] - dmax) <= 2e-4
+        assert np.max(np.abs(cols[f] - want)) <= 2e-5
+    # long rows (the app's default 32768-sample read -> 32764 bins)
+    xl = np.stack([synth.make("wbfm", 32768, seed=s) for s in range(2)])
+    dbl = ctx.psd(xl, epilogue=True)["db"]
+    cols, rng = ctx.spectrum_normalise(dbl, 200)
+    for f in range(2):
+        want, (dmin, dmax) = O.spectrum_normalise(O.psd_epilogue(O.psd_db(xl[f])), 200)
+        assert np.max(np.abs(cols[f] - want)) <= 2e-5
+
+
+def test_surface_row_vs_oracle(ctx):
+    x, ref_rows = make_rows(5, 4096)
+    W = 112
+    res = ctx.psd(x, epilogue=True, W=W, want_stats=True, want_db=False)
+    mag, _ = ctx.surface_row(res["cols"], res["stats"])
+    for f, r in enumerate(ref_rows):
+        want, _ = O.surface_row(r, W)
+        assert np.max(np.abs(mag[f] - want)) <= 1 and np.mean(mag[f] != want) <= 0.02
