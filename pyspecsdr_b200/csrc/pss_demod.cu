@@ -362,9 +362,78 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
         const int n_wi = (E + 30) / 31;                          // warp-iterations of 31 outputs each
         constexpr int PF = T == 32 ? 16 : 8;
         float2 pf[PF];
+        // tile ti covers chunks 1 + ti*T ..; its first discriminator index:
+        auto tile_g0 = [&](int ti) { return ti * T * q + 1 - lead; };
+        auto load_t = [&](int ti) {
+            const int g0 = tile_g0(ti);
+            if (g0 >= 0 && g0 + 31 * n_wi + 1 < D.N) tile_load<PF, false>(pf, x, g0, n_wi, D.N, warp, lane);
+            else tile_load<PF, true>(pf, x, g0, n_wi, D.N, warp, lane);
+        };
+        auto store_t = [&](int ti) {
+            const int g0 = tile_g0(ti);
+            float* dst = tile + (NBUF == 2 ? (ti & 1) * D.tile_floats : 0);
+            if (g0 >= 0 && g0 + 31 * n_wi + 1 < D.N)
+                tile_store<WFM, PF, false>(dst, pf, x, g0, E, n_wi, D.N, kc, D.scale, warp, lane);
+            else
+                tile_store<WFM, PF, true>(dst, pf, x, g0, E, n_wi, D.N, kc, D.scale, warp, lane);
+        };
+        // tensor half of a tile: a unit = (m-tile of 8 chunks, n-tile of 8 table rows) over the whole
+        // window.  MT*NT is 8 or 16 -> whole units per warp, plain stores.  MT=4, NT=3 (NFM, 32-chunk
+        // tiles): n-tiles 0/1 whole, the last n-tile (it only carries the yf-forcing row) split in two
+        // K halves -> atomics on that one column.
+        auto dmma_t = [&](int ti) {
+            const int j0 = 1 + ti * T;
+            const float* cur = tile + (NBUF == 2 ? (ti & 1) * D.tile_floats : 0);
+            constexpr int MT = T / 8, UNITS = MT * NT, NW = DEMOD_THREADS / 32;
+            constexpr bool SPLIT_LAST = (UNITS % NW) != 0 && MT == 4 && NT == 3;
+            constexpr int UPW = SPLIT_LAST ? 1 : (UNITS + NW - 1) / NW;      // whole units per warp
+#pragma unroll
+            for (int uu = 0; uu < UPW + (SPLIT_LAST ? 1 : 0); ++uu) {
+                int mt, nt, ks0 = 0, ks1 = D.KS;
+                bool atomic = false;
+                if (SPLIT_LAST) {
+                    mt = warp % MT;
+                    if (uu == 0) nt = warp / MT;
+                    else {
+                        nt = 2;
+                        atomic = true;
+                        ks0 = (warp / MT) ? D.KS / 2 : 0;
+                        ks1 = (warp / MT) ? D.KS : D.KS / 2;
+                    }
+                } else {
+                    const int unit = warp * UPW + uu;
+                    if (unit >= UNITS) break;
+                    mt = unit % MT;
+                    nt = unit / MT;
+                }
+                double c0 = 0.0, c1 = 0.0;
+                const float* arow = cur + (mt * 8 + (lane >> 2)) * q + (lane & 3);
+                const double* bp = tab + nt * 32 + lane;
+#pragma unroll 4
+                for (int ks = ks0; ks < ks1; ++ks)
+                    dmma_m8n8k4(c0, c1, (double)arow[4 * ks], bp[ks * NT * 32]);
+                const int j = j0 + mt * 8 + (lane >> 2);
+                const int col = nt * 8 + 2 * (lane & 3);
+                if (j <= n_body) {
+                    double* us = U + (size_t)j * ROWS;
+                    if (atomic) {
+                        if (col < ROWS) atomicAdd(us + col, c0);
+                        if (col + 1 < ROWS) atomicAdd(us + col + 1, c1);
+                    } else {
+                        if (col < ROWS) us[col] = c0;
+                        if (col + 1 < ROWS) us[col + 1] = c1;
+                    }
+                }
+            }
+        };
+        // Odd warps run the producer half (discriminator, ALU/LSU) of an iteration before the tensor
+        // half, even warps after it, so the two pipes overlap inside a CTA; an odd warp therefore keeps
+        // its IQ loads two tiles ahead.
+        const bool late = NBUF == 2 && SF == 8 && (warp & 1);      // measured: +4 % NFM, -2 % WFM
         if (n_tiles > 0) {
-            tile_load<PF, true>(pf, x, 1 - lead, n_wi, D.N, warp, lane);
-            tile_store<WFM, PF, true>(tile, pf, x, 1 - lead, E, n_wi, D.N, kc, D.scale, warp, lane);
+            load_t(0);
+            store_t(0);
+            if (late && n_tiles > 1) load_t(1);
         }
         __syncthreads();
         if (tid <= SF) {
@@ -374,71 +443,18 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
             else red[24] = acc;                  // yf at ext index 27
         }
 
-        // ---- body chunks: discriminator tile -> DMMA against the response tables.  The IQ loads of
-        // tile t+1 are issued before tile t is consumed by the tensor pipe; one barrier per tile.
+        // ---- body chunks: discriminator tile -> DMMA against the response tables; one barrier per tile
         for (int tl = 0; tl < n_tiles; ++tl) {
-            const int j0 = 1 + tl * T;
-            const float* cur = tile + (NBUF == 2 ? (tl & 1) * D.tile_floats : 0);
-            const int g_next = (j0 + T - 1) * q + 1 - lead;
             const bool more = tl + 1 < n_tiles;
-            // interior tile: every IQ index g_next .. g_next + 31*n_wi lies inside the block
-            const bool interior = g_next >= 0 && g_next + 31 * n_wi + 1 < D.N;
-            if (more) {
-                if (interior) tile_load<PF, false>(pf, x, g_next, n_wi, D.N, warp, lane);
-                else tile_load<PF, true>(pf, x, g_next, n_wi, D.N, warp, lane);
-            }
-            {
-                // work split over the 8 warps: a unit = (m-tile of 8 chunks, n-tile of 8 table rows)
-                // over the whole window.  MT*NT is 8 or 16 -> whole units per warp, plain stores.
-                // MT=4, NT=3 (NFM, 32-chunk tiles): n-tiles 0/1 whole, the last n-tile (it only
-                // carries the yf-forcing row) split in two K halves -> atomics on that one column.
-                constexpr int MT = T / 8, UNITS = MT * NT, NW = DEMOD_THREADS / 32;
-                constexpr bool SPLIT_LAST = (UNITS % NW) != 0 && MT == 4 && NT == 3;
-                constexpr int UPW = SPLIT_LAST ? 1 : (UNITS + NW - 1) / NW;      // whole units per warp
-#pragma unroll
-                for (int uu = 0; uu < UPW + (SPLIT_LAST ? 1 : 0); ++uu) {
-                    int mt, nt, ks0 = 0, ks1 = D.KS;
-                    bool atomic = false;
-                    if (SPLIT_LAST) {
-                        mt = warp % MT;
-                        if (uu == 0) nt = warp / MT;
-                        else {
-                            nt = 2;
-                            atomic = true;
-                            ks0 = (warp / MT) ? D.KS / 2 : 0;
-                            ks1 = (warp / MT) ? D.KS : D.KS / 2;
-                        }
-                    } else {
-                        const int unit = warp * UPW + uu;
-                        if (unit >= UNITS) break;
-                        mt = unit % MT;
-                        nt = unit / MT;
-                    }
-                    double c0 = 0.0, c1 = 0.0;
-                    const float* arow = cur + (mt * 8 + (lane >> 2)) * q + (lane & 3);
-                    const double* bp = tab + nt * 32 + lane;
-#pragma unroll 4
-                    for (int ks = ks0; ks < ks1; ++ks)
-                        dmma_m8n8k4(c0, c1, (double)arow[4 * ks], bp[ks * NT * 32]);
-                    const int j = j0 + mt * 8 + (lane >> 2);
-                    const int col = nt * 8 + 2 * (lane & 3);
-                    if (j <= n_body) {
-                        double* us = U + (size_t)j * ROWS;
-                        if (atomic) {
-                            if (col < ROWS) atomicAdd(us + col, c0);
-                            if (col + 1 < ROWS) atomicAdd(us + col + 1, c1);
-                        } else {
-                            if (col < ROWS) us[col] = c0;
-                            if (col + 1 < ROWS) us[col + 1] = c1;
-                        }
-                    }
-                }
-            }
-            if (NBUF == 1) __syncthreads();
-            if (more) {
-                float* nxt = tile + (NBUF == 2 ? ((tl + 1) & 1) * D.tile_floats : 0);
-                if (interior) tile_store<WFM, PF, false>(nxt, pf, x, g_next, E, n_wi, D.N, kc, D.scale, warp, lane);
-                else tile_store<WFM, PF, true>(nxt, pf, x, g_next, E, n_wi, D.N, kc, D.scale, warp, lane);
+            if (!late) {
+                if (more) load_t(tl + 1);
+                dmma_t(tl);
+                if (NBUF == 1) __syncthreads();
+                if (more) store_t(tl + 1);
+            } else {
+                if (more) store_t(tl + 1);
+                if (tl + 2 < n_tiles) load_t(tl + 2);
+                dmma_t(tl);
             }
             __syncthreads();
         }
