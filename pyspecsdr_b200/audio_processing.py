@@ -1,30 +1,38 @@
-"""Drop-in for the numeric line of PySpecSDR's `audio_processing` module.
+"""Drop-in for the arithmetic of PySpecSDR's `audio_processing` module.
 
-Only `write_audio_samples` contains arithmetic (audio_processing.py:34-38); the PortAudio probe and
-the WAV open/close are host I/O and stay as they are in the reference (out of scope).
+The only numeric line there is the float -> int16 pack inside `write_audio_samples`
+(audio_processing.py:36-38, repeated in io_manager.py:25-26); it runs on the GPU here
+(`pss_audio_to_int16`).  The PortAudio probe (`init_audio_device`) is hardware I/O and is not provided:
+keep importing it from the reference module.  The WAV container handling below exists only so that
+`write_audio_samples(wav_file, samples)` can be exercised end to end.
 """
+from __future__ import annotations
+
 import wave
 
 import numpy as np
 
-from . import signal_processing as _sp
+from . import signal_processing as _dsp
 from .filters import AUDIO_RATE as DEFAULT_SAMPLE_RATE
 
+_STEREO, _PCM16_BYTES = 2, 2
 
-def start_audio_recording(filename, sample_rate=DEFAULT_SAMPLE_RATE):
-    """audio_processing.py:24-31 (unchanged host I/O)."""
-    wav_file = wave.open(filename, 'wb')
-    wav_file.setnchannels(2)
-    wav_file.setsampwidth(2)
-    wav_file.setframerate(sample_rate)
-    return wav_file
+
+def pcm16(samples) -> np.ndarray:
+    """np.int16(samples * 32767) with C truncation, computed by the int16 kernel."""
+    return _dsp._ctx().to_int16(np.asarray(samples))
 
 
 def write_audio_samples(wav_file, samples):
-    """audio_processing.py:34-38: the float -> int16 pack runs on the GPU."""
-    wav_file.writeframes(_sp._ctx().to_int16(np.asarray(samples)).tobytes())
+    """Same call as the reference: append one block of float audio to an open 16-bit WAV."""
+    wav_file.writeframes(pcm16(samples).tobytes())
+
+
+def start_audio_recording(filename, sample_rate=DEFAULT_SAMPLE_RATE):
+    sink = wave.open(filename, "wb")
+    sink.setparams((_STEREO, _PCM16_BYTES, int(sample_rate), 0, "NONE", "not compressed"))
+    return sink
 
 
 def stop_audio_recording(wav_file):
-    """audio_processing.py:41-43."""
     wav_file.close()
