@@ -132,7 +132,7 @@ class Context:
         return int(lib.pss_kernel_launches(self._h))
 
     # ------------------------------------------------------------------ PSD (host arrays)
-    def psd(self, samples, window="hamming", epilogue=False, W=0, want_stats=False, want_db=True):
+    def psd(self, samples, window="hamming", epilogue=False, W=0, want_stats=False, want_db=True, fp32=False):
         """Batched compute_fft (+ optional main-loop epilogue).  Returns dict of float32 arrays:
         db [F, N or N-4], cols [F, W], stats [F, 4] (max, mean, finite-min, finite-max)."""
         x = _as_frames(samples)
@@ -150,15 +150,16 @@ class Context:
         if want_stats:
             res["stats"] = np.empty((F, 4), np.float32)
             out.stats = res["stats"].ctypes.data
-        self._ck(lib.pss_psd_c64(self._h, x.ctypes.data, N, F, WINDOWS[window], 1 if epilogue else 0, 0,
-                                 C.byref(out)), "pss_psd_c64")
+        self._ck(lib.pss_psd_c64(self._h, x.ctypes.data, N, F, WINDOWS[window], 1 if epilogue else 0,
+                                 1 if fp32 else 0, C.byref(out)), "pss_psd_c64")
         return res
 
-    def psd_dev(self, iq, N, n_frames, db=None, window="hamming", epilogue=False, cols=None, W=0, stats=None):
+    def psd_dev(self, iq, N, n_frames, db=None, window="hamming", epilogue=False, cols=None, W=0, stats=None,
+                fp32=False):
         """Device-pointer PSD: enqueue only.  `iq`, `db`, `cols`, `stats` are device buffers."""
         out = PsdOut(_ptr(db), _ptr(cols), W, _ptr(stats))
-        self._ck(lib.pss_psd_c64_dev(self._h, _ptr(iq), N, n_frames, WINDOWS[window], 1 if epilogue else 0, 0,
-                                     C.byref(out)), "pss_psd_c64_dev")
+        self._ck(lib.pss_psd_c64_dev(self._h, _ptr(iq), N, n_frames, WINDOWS[window], 1 if epilogue else 0,
+                                     1 if fp32 else 0, C.byref(out)), "pss_psd_c64_dev")
 
     # ------------------------------------------------------------------ scanner
     def scan(self, frames, rel_db=20.0, threshold=None, want_rows=False):

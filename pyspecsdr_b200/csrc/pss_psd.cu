@@ -38,7 +38,7 @@ struct PsdCfg {
     static constexpr int TPF = N / 16;                       // threads per frame
     static constexpr int THREADS = TPF > 256 ? TPF : 256;
     static constexpr int FPC = THREADS / TPF;                // frames per CTA
-    static constexpr int MINB = (sizeof(T) * 2 * N * FPC <= 64 * 1024) ? 2 : 1;
+    static constexpr int MINB = (sizeof(T) * 2 * N * FPC <= 32 * 1024) ? 4 : (sizeof(T) * 2 * N * FPC <= 64 * 1024) ? 2 : 1;
     static constexpr size_t SMEM = (size_t)FPC * N * sizeof(cx<T>);
     static constexpr int NP = pss_num_passes(LOG2N);
 };
@@ -145,8 +145,15 @@ psd_kernel(const PsdParams p) {
 
     // ---- |X|^2 -> dB at the fft-shifted position
     auto emit = [&](int k, const cx<T> X) {
-        const double pw = (double)X.x * (double)X.x + ((double)X.y * (double)X.y + 1e-10);
-        const float d = db_from_power(pw);
+        float d;
+        if constexpr (sizeof(T) == 8) {
+            d = db_from_power((double)X.x * (double)X.x + ((double)X.y * (double)X.y + 1e-10));
+        } else {            // PSS_PREC_FP32 fast mode: the whole chain in float (does NOT meet 1e-4 dB)
+            const float pf = (float)X.x * (float)X.x + ((float)X.y * (float)X.y + 1e-10f);
+            float l;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(pf));
+            d = 3.01029995663981195f * l;
+        }
         const int pos = k ^ (N >> 1);
         if constexpr (LOG2N1 > 0) {
             const long long fb = frame >> LOG2N1;
@@ -675,13 +682,14 @@ static int ilog2_exact(int n) {
     return l;
 }
 
-static int get_tables(pss_ctx* ctx, int log2n, pss_fft_tables** out) {
-    auto it = ctx->fft_tables.find(log2n);
+static int get_tables(pss_ctx* ctx, int log2n, pss_fft_tables** out, bool fp32 = false) {
+    const int key = log2n + (fp32 ? 1000 : 0);
+    auto it = ctx->fft_tables.find(key);
     if (it == ctx->fft_tables.end()) {
         pss_fft_tables tab;
-        int rc = build_tables<double>(ctx, log2n, tab);
+        int rc = fp32 ? build_tables<float>(ctx, log2n, tab) : build_tables<double>(ctx, log2n, tab);
         if (rc != PSS_OK) return rc;
-        it = ctx->fft_tables.emplace(log2n, tab).first;
+        it = ctx->fft_tables.emplace(key, tab).first;
     }
     *out = &it->second;
     return PSS_OK;
@@ -789,7 +797,7 @@ extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_f
     if (!ctx || !iq || !out || n_frames < 0) return PSS_ERR_ARG;
     if (window < 0 || window > 2 || (epilogue != PSS_EPI_RAW && epilogue != PSS_EPI_SMOOTH_CLAMP))
         return PSS_ERR_ARG;
-    if (precision != PSS_PREC_FP64) return PSS_ERR_UNSUPPORTED;
+    if (precision != PSS_PREC_FP64 && precision != PSS_PREC_FP32) return PSS_ERR_ARG;
     if (epilogue == PSS_EPI_RAW && !out->db) return PSS_ERR_ARG;
     if (epilogue == PSS_EPI_RAW && (out->cols || out->stats)) return PSS_ERR_UNSUPPORTED;
     if (out->cols && out->W < 1) return PSS_ERR_ARG;
@@ -797,9 +805,12 @@ extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_f
     if (log2n < 0) return PSS_ERR_UNSUPPORTED;
     if (n_frames == 0) return PSS_OK;
     if (n_frames > 0x7fffffffLL) return PSS_ERR_ARG;
+    const bool fp32 = precision == PSS_PREC_FP32;
+    // the float fast mode exists for the plain spectrum only (it cannot meet the 1e-4 dB bar, see pss.h)
+    if (fp32 && (epilogue != PSS_EPI_RAW || log2n > 13)) return PSS_ERR_UNSUPPORTED;
     if (log2n > 13) return psd_large(ctx, iq, log2n, n_frames, window, epilogue, out);
     pss_fft_tables* tab;
-    int rc = get_tables(ctx, log2n, &tab);
+    int rc = get_tables(ctx, log2n, &tab, fp32);
     if (rc != PSS_OK) return rc;
     PsdParams p{};
     p.iq = reinterpret_cast<const float2*>(iq);
@@ -810,6 +821,7 @@ extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_f
     p.cols = out->cols;
     p.W = out->W;
     p.stats = out->stats;
+    if (fp32) return launch_by_n<float, EPI_RAW>(ctx, log2n, p);
     if (epilogue == PSS_EPI_RAW) return launch_by_n<double, EPI_RAW>(ctx, log2n, p);
     return launch_by_n<double, EPI_SMOOTH>(ctx, log2n, p);
 }
