@@ -111,6 +111,17 @@ int pss_scan_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_steps, int 
 int pss_spectrum_normalise(pss_ctx* ctx, const float* db, int n_bins, int64_t n_frames, int W, float* cols,
                            float* range);
 
+/* Glyph / colour index planes of the draw_* functions from normalised values
+ * (pss_display_render output), so the TUI can paint one string per row instead of a Python loop per
+ * cell.  kind: WATERFALL  a = glyph level 0..3 ('.', '-', '=', '#'; pyspecsdr.py:1390-1397), b = int(v*5) (:1388)
+ *             GRADIENT   a = int(v*8) index into ' ._-=+*#@' (:1691),            b = int(v*5) (:1695)
+ *             PERSISTENCE a = screen row int((1-v)*(H-1)) (:1556)               b = int(v*5)
+ *             SURFACE    a = magnitude int(v*20) (:1593)                         b = int(v*5)
+ * NaN inputs (rows older than the history) give 255.  plane_b may be NULL. */
+enum { PSS_QUANT_WATERFALL = 0, PSS_QUANT_GRADIENT = 1, PSS_QUANT_PERSISTENCE = 2, PSS_QUANT_SURFACE = 3 };
+int pss_display_quantise(pss_ctx* ctx, const float* norm, int64_t n, int kind, int H, uint8_t* plane_a,
+                         uint8_t* plane_b);
+
 /* ------------------------------------------------------------------ demodulation
  * Replaces demodulate_signal(samples, sample_rate, mode)  signal_processing.py:220-240 and the
  * per-mode chains demodulate_nfm :91-116, demodulate_wfm :119-176 (+ iq_correction :46-80),

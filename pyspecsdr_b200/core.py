@@ -318,3 +318,15 @@ class Context:
         and its min/max: magnitude = int(normalised * 20)."""
         norm, mm = self.display_render(cols, stats, rows_max=1, guard_zero_range=True)
         return (norm[:, 0].astype(np.float64) * 20).astype(np.int64), mm
+
+    QUANT = {"waterfall": 0, "gradient": 1, "persistence": 2, "surface": 3}
+
+    def display_quantise(self, norm, kind: str = "waterfall", H: int = 0):
+        """Glyph / colour index planes (uint8, 255 = no data) of the draw_* functions from normalised
+        values; see pss_display_quantise in include/pss.h."""
+        v = np.ascontiguousarray(norm, dtype=np.float32)
+        a = np.empty(v.shape, np.uint8)
+        b = np.empty(v.shape, np.uint8)
+        self._ck(lib.pss_display_quantise(self._h, v.ctypes.data, v.size, self.QUANT[kind], H, a.ctypes.data,
+                                          b.ctypes.data), "pss_display_quantise")
+        return a, b

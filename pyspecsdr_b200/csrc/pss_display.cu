@@ -85,6 +85,27 @@ spectrum_normalise_kernel(const float* __restrict__ db, const int n, const long 
     }
 }
 
+// Glyph / colour index planes of the draw_* functions from normalised values.
+// int() in the reference truncates toward zero; NaN (rows older than the history) -> 255.
+__global__ void display_quantise_kernel(const float* __restrict__ norm, const long long n, const int kind,
+                                        const int H, uint8_t* __restrict__ a, uint8_t* __restrict__ b) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = norm[i];
+    if (v != v) {
+        a[i] = 255;
+        if (b) b[i] = 255;
+        return;
+    }
+    int pa, pb = (int)(v * 5.f);                                      // colour_index, :1388 / :1695
+    if (kind == PSS_QUANT_WATERFALL) pa = (v > 0.25f) + (v > 0.5f) + (v > 0.75f);          // '.', '-', '=', '#' :1390-1397
+    else if (kind == PSS_QUANT_GRADIENT) pa = (int)(v * 8.f);                              // ' ._-=+*#@' :1691
+    else if (kind == PSS_QUANT_PERSISTENCE) pa = (int)((1.f - v) * (float)(H - 1));        // screen row :1556
+    else pa = (int)(v * 20.f);                                                             // surface magnitude :1593
+    a[i] = (uint8_t)min(max(pa, 0), 254);
+    if (b) b[i] = (uint8_t)min(max(pb, 0), 254);
+}
+
 void pss_display_release(pss_ctx*) {}
 
 extern "C" {
@@ -128,6 +149,26 @@ int pss_display_render(pss_ctx* ctx, const float* cols, const float* stats, int 
     return PSS_OK;
 }
 
+
+int pss_display_quantise(pss_ctx* ctx, const float* norm, int64_t n, int kind, int H, uint8_t* plane_a,
+                         uint8_t* plane_b) {
+    if (!ctx || !norm || !plane_a || n < 0 || kind < 0 || kind > 3) return PSS_ERR_ARG;
+    if (kind == PSS_QUANT_PERSISTENCE && H < 2) return PSS_ERR_ARG;
+    if (n == 0) return PSS_OK;
+    PSS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_in, &ctx->d_in_bytes, (size_t)n * 4))) return rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_out, &ctx->d_out_bytes, (size_t)n * 2))) return rc;
+    uint8_t* da = (uint8_t*)ctx->d_out;
+    uint8_t* db = plane_b ? da + n : nullptr;
+    PSS_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, norm, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    display_quantise_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const float*)ctx->d_in, n, kind, H, da, db);
+    PSS_LAUNCH_CHECK(ctx);
+    PSS_CUDA(ctx, cudaMemcpyAsync(plane_a, da, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    if (plane_b) PSS_CUDA(ctx, cudaMemcpyAsync(plane_b, db, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    PSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PSS_OK;
+}
 
 int pss_spectrum_normalise(pss_ctx* ctx, const float* db, int n_bins, int64_t n_frames, int W, float* cols,
                            float* range) {

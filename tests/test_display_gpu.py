@@ -105,3 +105,31 @@ def test_surface_row_vs_oracle(ctx):
     for f, r in enumerate(ref_rows):
         want, _ = O.surface_row(r, W)
         assert np.max(np.abs(mag[f] - want)) <= 1 and np.mean(mag[f] != want) <= 0.02
+
+
+def test_display_quantised_planes_vs_oracle(ctx):
+    """8f-3: glyph / colour planes (what the reference computes per cell in Python loops)."""
+    x, ref_rows = make_rows(32, 4096)
+    W, H = 112, 36
+    res = ctx.psd(x, epilogue=True, W=W, want_stats=True, want_db=False)
+    norm, _ = ctx.display_render(res["cols"], res["stats"], rows_max=30)
+    level, colour = ctx.display_quantise(norm[-1], "waterfall")
+    hist = []
+    for r in ref_rows:
+        want_norm, _, want_colour, want_level = O.waterfall_accumulate(hist, r, W)
+    assert np.mean(level != want_level) <= 1e-3 and np.mean(colour != want_colour) <= 1e-3
+    gnorm, _ = ctx.display_render(res["cols"], res["stats"], rows_max=30, guard_zero_range=True)
+    chars, colour = ctx.display_quantise(gnorm[-1], "gradient")
+    hist = []
+    for r in ref_rows:
+        _, _, want_chars, want_colour = O.gradient_accumulate(hist, r, W)
+    assert np.mean(chars != want_chars) <= 1e-3 and np.mean(colour != want_colour) <= 1e-3
+    # rows older than the history are marked 255
+    early, _ = ctx.display_quantise(norm[2], "waterfall")
+    assert np.all(early[3:] == 255) and np.all(early[:3] < 4)
+    pn, _ = ctx.display_render(res["cols"][:10], res["stats"][:10], rows_max=10, guard_zero_range=True)
+    ys, _ = ctx.display_quantise(pn[-1][::-1], "persistence", H=H)
+    hist = []
+    for r in ref_rows[:10]:
+        want_ys, _, _ = O.persistence_accumulate(hist, r, W, H)
+    assert np.mean(ys != want_ys) <= 2e-3 and np.max(np.abs(ys.astype(int) - want_ys)) <= 1

@@ -146,3 +146,22 @@ def test_scanner_gather_world2_gloo_bitwise_equals_single_rank():
         np.testing.assert_array_equal(gp, want_peak)
         np.testing.assert_array_equal(gc, want_count)
         np.testing.assert_array_equal(gr, want_rows)
+
+
+# ------------------------------------------------------------------ capture files
+def test_capture_block_ranges_and_format(tmp_path):
+    from pyspecsdr_b200 import capture
+    x = synth.make("wbfm", 5 * 4096 + 100, seed=1)
+    path = str(tmp_path / "cap.npy")
+    np.save(path, x)                                        # what record_signal does, pyspecsdr.py:816
+    cap = capture.open_capture(path)
+    assert cap.dtype == np.complex64 and len(cap) == len(x)
+    assert capture.block_range(len(cap), 4096) == (0, 5)    # trailing partial read is dropped
+    parts = [capture.block_range(len(cap), 4096, r, 2) for r in range(2)]
+    assert parts == [(0, 2), (2, 5)]
+    got = [v for _, v in capture.iter_chunks(cap, 4096, 0, 5, 2)]
+    assert [len(v) for v in got] == [2, 2, 1]
+    np.testing.assert_array_equal(np.concatenate(got).ravel(), x[:5 * 4096])
+    np.save(path, x.astype(np.complex128))
+    with pytest.raises(ValueError):
+        capture.open_capture(path)
