@@ -41,6 +41,8 @@ class DemodPlan:
     def __init__(self, ctx: "Context", mode: str, fs: float, N: int):
         self.ctx, self.mode, self.fs, self.N = ctx, mode, float(fs), int(N)
         desc = DemodDesc()
+        if mode not in filters.MODES:
+            raise ValueError(f"no demodulation plan for mode {mode!r}")
         desc.mode = filters.MODES[mode]
         desc.N = N
         keep = []
