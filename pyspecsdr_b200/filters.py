@@ -58,6 +58,10 @@ def wfm_pre_sos(fs: float) -> np.ndarray:
     """L+R low-pass (:126), the /2 of :140-141 (L-R is identically ~0) and the 75 us
     de-emphasis one-pole (:144-149) as one cascade of 4 sections."""
     lp = butter_sos(0, 15000, fs)
+    # the reference also designs the pilot (:129) and L-R (:133) band-passes; their outputs are
+    # multiplied by ~0, but the designs raise ValueError when 53 kHz is not below Nyquist, and so do we
+    butter_sos(19000 - 200, 19000 + 200, fs)
+    butter_sos(38000 - 15000, 38000 + 15000, fs)
     a = math.exp(-1 / (75e-6 * fs))
     de = np.array([[0.5 * (1 - a), 0.0, 0.0, 1.0, -a, 0.0]])
     return np.vstack([lp, de])

@@ -19,6 +19,9 @@ DECIM_CASES = [
     ("WFM", "wbfm", 32768, 2.4e6), ("WFM", "noise", 32768, 2.4e6), ("WFM", "wbfm", 16385, 1.024e6),
     ("NFM", "wbfm", 8192, 250e3), ("WFM", "wbfm", 4000, 1e6), ("NFM", "tone40", 32768, 1e6),
     ("WFM", "wbfm", 65536, 2.4e6),
+    # extremes: q = 907 (20 MS/s, response table too large for shared memory) and q = 2 (48 kS/s, the
+    # FIR history spans 32 chunks and the tail block carries many outputs)
+    ("NFM", "wbfm", 65536, 20e6), ("WFM", "wbfm", 65536, 20e6), ("NFM", "wbfm", 4096, 48000.0),
 ]
 
 
@@ -99,3 +102,12 @@ def test_frame_demod_golden(ctx, golden):
 def test_usb_equals_lsb_on_gpu(ctx):
     x = synth.make("ssb", 8192, seed=4)
     np.testing.assert_array_equal(ctx.demod(x, 1e6, "USB"), ctx.demod(x, 1e6, "LSB"))
+
+
+def test_wfm_below_106k_raises_like_the_reference(ctx):
+    # the reference's 23-53 kHz band-pass design fails when 53 kHz >= fs/2; same exception type here
+    x = synth.make("noise", 2048, seed=0)
+    with pytest.raises(ValueError):
+        O.demod(x, 48000.0, "WFM")
+    with pytest.raises(ValueError):
+        ctx.demod(x, 48000.0, "WFM")
