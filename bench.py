@@ -161,6 +161,32 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ----------------------------------------------------------------------------- NUMA placement
+def bind_to_gpu_numa_node(device_index):
+    """Pin this rank's CPU affinity to the NUMA node its GPU hangs off (sysfs), so the pinned staging
+    buffers it allocates next are node-local and N ranks do not all pull their host->device copies
+    across the inter-socket link.  Returns (original affinity, note); no-op when sysfs lacks the info."""
+    try:
+        import torch
+        orig = os.sched_getaffinity(0)
+        pr = torch.cuda.get_device_properties(device_index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return orig, "numa_node=-1 (single node or not exposed)"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= orig
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return orig, f"bound to NUMA node {node} ({len(cpus)} cpus)"
+        return orig, f"NUMA node {node} has no allowed cpus"
+    except Exception as e:                                    # never fail the bench over placement
+        return None, f"not bound ({type(e).__name__})"
+
+
 # ----------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -340,6 +366,7 @@ def main():
                   "checked_blocks": 2, "ok": bool(rms <= 1e-5 and dberr <= 1e-4)}
 
     # ---- e2e: host-pointer C ABI, pinned host buffers, copies in the timed region (every rank)
+    orig_affinity, numa_note = bind_to_gpu_numa_node(local_rank)
     nb_e = nb
     host_iq = ctx.pinned_empty((nb_e, N_BLOCK), np.complex64)
     host_iq.view(np.float32).reshape(nb_e, N_BLOCK, 2)[:] = iq[:nb_e].cpu().numpy()
@@ -362,9 +389,11 @@ def main():
     d2h = sum(v.nbytes for v in outs.values())
     e2e = {"value": world * nb_e * N_BLOCK / e2e_ms / 1e3, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": args.e2e_steps,
-           "api": "pss_pipeline_c64 (host pointers, pinned)",
+           "api": "pss_pipeline_c64 (host pointers, pinned)", "host_placement": numa_note,
            "audio_matches_device_path": bool(np.array_equal(outs["audio"][:2], audio[:2].cpu().numpy()))}
 
+    if orig_affinity:
+        os.sched_setaffinity(0, orig_affinity)               # the CPU baseline uses every host core
     if rank == 0 and not args.no_cpu:
         hb = np.ascontiguousarray(host_iq[:args.cpu_blocks])
         ref = CpuReference(hb, args.mode)
