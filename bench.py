@@ -260,6 +260,7 @@ def main():
     norm = torch.empty(nb, ROWS_MAX, W_COLS, device=dev, dtype=torch.float32)
     minmax = torch.empty(nb, 2, device=dev, dtype=torch.float32)
     audio = torch.empty(nb, plan.out_len, plan.channels, device=dev, dtype=torch.float32)
+    moments = torch.empty(F, 4, device=dev, dtype=torch.float64)     # PSD by-product consumed by the WFM demod
     torch.cuda.synchronize()
 
     names = ["psd_kernel<12,f64,smooth>", "display_render_kernel", f"demod_decim_kernel<{args.mode}>"]
@@ -267,14 +268,15 @@ def main():
     def step(ev=None):
         if ev is not None:
             ev[0].record(stream)
-        ctx.psd_dev(iq, N_FFT, F, db=db, window="hamming", epilogue=True, cols=cols, W=W_COLS, stats=stats)
+        ctx.psd_dev(iq, N_FFT, F, db=db, window="hamming", epilogue=True, cols=cols, W=W_COLS, stats=stats,
+                    moments=moments)
         if ev is not None:
             ev[1].record(stream)
         ctx.display_render_dev(cols, stats, W_COLS, F, norm, minmax, rows_max=ROWS_MAX, first=fpb - 1, step=fpb,
                                n_renders=nb)
         if ev is not None:
             ev[2].record(stream)
-        ctx.demod_dev(plan, iq, nb, audio)
+        ctx.demod_dev(plan, iq, nb, audio, moments=moments, frames_per_block=fpb)
         if ev is not None:
             ev[3].record(stream)
 

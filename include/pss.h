@@ -83,6 +83,10 @@ typedef struct {
     float* cols;    /* [n_frames][W] rows resampled to W columns (np.interp semantics), or NULL */
     int    W;
     float* stats;   /* [n_frames][4] = max, mean, finite-min, finite-max of the row, or NULL */
+    double* moments; /* [n_frames][4] = sum I^2, sum Q^2, sum I*Q, 0 of the frame's samples, or NULL (N >= 512,
+                        N <= 8192).  A by-product of the pass that already reads the IQ: feeding it to
+                        pss_demod_c64_dev_moments saves the WFM demodulator its own iq_correction pass over
+                        the block (signal_processing.py:52-61 need exactly these sums). */
 } pss_psd_out;
 
 int pss_psd_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, int window, int epilogue,
@@ -184,6 +188,11 @@ int  pss_demod_plan_channels(const pss_demod_plan* plan);
 int  pss_demod_c64(pss_ctx* ctx, pss_demod_plan* plan, const float* iq, int64_t n_frames, float* audio);
 int  pss_demod_c64_dev(pss_ctx* ctx, pss_demod_plan* plan, const float* iq, int64_t n_frames,
                        float* audio);
+/* As pss_demod_c64_dev, with the I/Q second moments of every block supplied as `frames_per_block`
+ * consecutive rows of a PSD call's `moments` output over the same IQ (device pointer).  Used by WFM
+ * plans (iq_correction); ignored by the others. */
+int  pss_demod_c64_dev_moments(pss_ctx* ctx, pss_demod_plan* plan, const float* iq, int64_t n_frames,
+                               float* audio, const double* moments, int frames_per_block);
 
 /* ------------------------------------------------------------------ display accumulate
  * Replaces the numeric part of draw_waterfall (pyspecsdr.py:1351-1358, 1373-1398),

@@ -17,7 +17,8 @@ class PssError(RuntimeError):
 
 
 class PsdOut(C.Structure):
-    _fields_ = [("db", C.c_void_p), ("cols", C.c_void_p), ("W", C.c_int), ("stats", C.c_void_p)]
+    _fields_ = [("db", C.c_void_p), ("cols", C.c_void_p), ("W", C.c_int), ("stats", C.c_void_p),
+                ("moments", C.c_void_p)]
 
 
 class DemodDesc(C.Structure):
@@ -76,6 +77,7 @@ def _signatures():
         "pss_demod_plan_channels": (i32, [vp]),
         "pss_demod_c64": (i32, [vp, vp, vp, i64, vp]),
         "pss_demod_c64_dev": (i32, [vp, vp, vp, i64, vp]),
+        "pss_demod_c64_dev_moments": (i32, [vp, vp, vp, i64, vp, vp, i32]),
     }
 
 

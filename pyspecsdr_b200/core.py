@@ -157,9 +157,9 @@ class Context:
         return res
 
     def psd_dev(self, iq, N, n_frames, db=None, window="hamming", epilogue=False, cols=None, W=0, stats=None,
-                fp32=False):
-        """Device-pointer PSD: enqueue only.  `iq`, `db`, `cols`, `stats` are device buffers."""
-        out = PsdOut(_ptr(db), _ptr(cols), W, _ptr(stats))
+                fp32=False, moments=None):
+        """Device-pointer PSD: enqueue only.  `iq`, `db`, `cols`, `stats`, `moments` are device buffers."""
+        out = PsdOut(_ptr(db), _ptr(cols), W, _ptr(stats), _ptr(moments))
         self._ck(lib.pss_psd_c64_dev(self._h, _ptr(iq), N, n_frames, WINDOWS[window], 1 if epilogue else 0,
                                      1 if fp32 else 0, C.byref(out)), "pss_psd_c64_dev")
 
@@ -198,8 +198,14 @@ class Context:
         self._ck(lib.pss_demod_c64(self._h, plan._h, x.ctypes.data, F, out.ctypes.data), f"pss_demod_c64({mode})")
         return out
 
-    def demod_dev(self, plan: DemodPlan, iq, n_frames: int, audio):
-        self._ck(lib.pss_demod_c64_dev(self._h, plan._h, _ptr(iq), n_frames, _ptr(audio)), "pss_demod_c64_dev")
+    def demod_dev(self, plan: DemodPlan, iq, n_frames: int, audio, moments=None, frames_per_block=0):
+        """Device-pointer demodulation.  `moments` = the PSD call's per-frame I/Q moments over the same
+        IQ (frames_per_block rows per block): lets a WFM plan skip its own iq_correction pass."""
+        if moments is None:
+            self._ck(lib.pss_demod_c64_dev(self._h, plan._h, _ptr(iq), n_frames, _ptr(audio)), "pss_demod_c64_dev")
+        else:
+            self._ck(lib.pss_demod_c64_dev_moments(self._h, plan._h, _ptr(iq), n_frames, _ptr(audio), _ptr(moments),
+                                                   frames_per_block), "pss_demod_c64_dev_moments")
 
     # ------------------------------------------------------------------ display accumulate
     def display_render(self, cols, stats, rows_max=30, first=0, step=1, n_renders=None, guard_zero_range=False):

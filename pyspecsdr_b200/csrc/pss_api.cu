@@ -148,6 +148,7 @@ int pss_psd_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, int wind
     dev.db = out->db ? (float*)ctx->d_out : nullptr;
     dev.cols = out->cols ? (float*)ctx->d_aux : nullptr;
     dev.stats = out->stats ? (float*)ctx->d_aux2 : nullptr;
+    dev.moments = nullptr;                 // a device-side by-product; not copied back by the host variant
     rc = pss_psd_c64_dev(ctx, (const float*)ctx->d_in, N, n_frames, window, epilogue, precision, &dev);
     if (rc) return rc;
     if (db_b) PSS_CUDA(ctx, cudaMemcpyAsync(out->db, dev.db, db_b, cudaMemcpyDeviceToHost, ctx->stream));

@@ -272,7 +272,8 @@ __device__ void blocked_scan(double* U, const int rows, const int foff, const in
 template <int SF, int T, int NBUF>
 __global__ void __launch_bounds__(DEMOD_THREADS, 2)
 demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __restrict__ audio,
-                   const long long n_frames, double* __restrict__ U_global) {
+                   const long long n_frames, double* __restrict__ U_global, const double* __restrict__ moments,
+                   const int mom_fpb) {
     constexpr bool WFM = SF == 16;
     constexpr int SB = 8, ROWS = SF + SB + 1, NT = (ROWS + 7) / 8;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -303,42 +304,52 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
             // second moments over the block (fp64 accumulation), then iq_correction's estimates
             // (per-thread float partials over N/256 samples, combined in fp64: the same order of
             // rounding error as numpy's own float32 pairwise means at :52, :60, :61)
-            float fii[4] = {0.f, 0.f, 0.f, 0.f}, fqq[4] = {0.f, 0.f, 0.f, 0.f}, fiq[4] = {0.f, 0.f, 0.f, 0.f};
-            int i = tid;
-            for (; i + 15 * DEMOD_THREADS < D.N; i += 16 * DEMOD_THREADS) {
-                float2 v[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u) v[u] = __ldg(x + i + u * DEMOD_THREADS);   // 16 loads in flight
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    fii[u & 3] = fmaf(v[u].x, v[u].x, fii[u & 3]);
-                    fqq[u & 3] = fmaf(v[u].y, v[u].y, fqq[u & 3]);
-                    fiq[u & 3] = fmaf(v[u].x, v[u].y, fiq[u & 3]);
-                }
-            }
-            for (; i < D.N; i += DEMOD_THREADS) {
-                const float2 s = __ldg(x + i);
-                fii[0] = fmaf(s.x, s.x, fii[0]);
-                fqq[0] = fmaf(s.y, s.y, fqq[0]);
-                fiq[0] = fmaf(s.x, s.y, fiq[0]);
-            }
-            double sii = ((double)fii[0] + (double)fii[1]) + ((double)fii[2] + (double)fii[3]);
-            double sqq = ((double)fqq[0] + (double)fqq[1]) + ((double)fqq[2] + (double)fqq[3]);
-            double siq = ((double)fiq[0] + (double)fiq[1]) + ((double)fiq[2] + (double)fiq[3]);
-            sii = warp_sum(sii);
-            sqq = warp_sum(sqq);
-            siq = warp_sum(siq);
-            if (lane == 0) {
-                red[warp] = sii;
-                red[8 + warp] = sqq;
-                red[16 + warp] = siq;
-            }
-            __syncthreads();
             double a = 0, b = 0, c = 0;
-            for (int w = 0; w < DEMOD_THREADS / 32; ++w) {
-                a += red[w];
-                b += red[8 + w];
-                c += red[16 + w];
+            if (moments) {
+                // the PSD kernel already summed I^2, Q^2, IQ per FFT frame while it read this block
+                const double* m = moments + (size_t)frame * mom_fpb * 4;
+                for (int k = 0; k < mom_fpb; ++k) {
+                    a += m[4 * k];
+                    b += m[4 * k + 1];
+                    c += m[4 * k + 2];
+                }
+            } else {
+                float fii[4] = {0.f, 0.f, 0.f, 0.f}, fqq[4] = {0.f, 0.f, 0.f, 0.f}, fiq[4] = {0.f, 0.f, 0.f, 0.f};
+                int i = tid;
+                for (; i + 15 * DEMOD_THREADS < D.N; i += 16 * DEMOD_THREADS) {
+                    float2 v[16];
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) v[u] = __ldg(x + i + u * DEMOD_THREADS);   // 16 loads in flight
+#pragma unroll
+                    for (int u = 0; u < 16; ++u) {
+                        fii[u & 3] = fmaf(v[u].x, v[u].x, fii[u & 3]);
+                        fqq[u & 3] = fmaf(v[u].y, v[u].y, fqq[u & 3]);
+                        fiq[u & 3] = fmaf(v[u].x, v[u].y, fiq[u & 3]);
+                    }
+                }
+                for (; i < D.N; i += DEMOD_THREADS) {
+                    const float2 s = __ldg(x + i);
+                    fii[0] = fmaf(s.x, s.x, fii[0]);
+                    fqq[0] = fmaf(s.y, s.y, fqq[0]);
+                    fiq[0] = fmaf(s.x, s.y, fiq[0]);
+                }
+                double sii = ((double)fii[0] + (double)fii[1]) + ((double)fii[2] + (double)fii[3]);
+                double sqq = ((double)fqq[0] + (double)fqq[1]) + ((double)fqq[2] + (double)fqq[3]);
+                double siq = ((double)fiq[0] + (double)fiq[1]) + ((double)fiq[2] + (double)fiq[3]);
+                sii = warp_sum(sii);
+                sqq = warp_sum(sqq);
+                siq = warp_sum(siq);
+                if (lane == 0) {
+                    red[warp] = sii;
+                    red[8 + warp] = sqq;
+                    red[16 + warp] = siq;
+                }
+                __syncthreads();
+                for (int w = 0; w < DEMOD_THREADS / 32; ++w) {
+                    a += red[w];
+                    b += red[8 + w];
+                    c += red[16 + w];
+                }
             }
             const double n = (double)D.N;
             const float q_amp = (float)sqrt(2.0 * b / n);                        // :52
@@ -620,7 +631,8 @@ static int create_decim(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
     return PSS_OK;
 }
 
-static int launch_decim(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t n_frames, float* audio) {
+static int launch_decim(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t n_frames, float* audio,
+                        const double* moments = nullptr, int mom_fpb = 0) {
     DecimDev& D = pl->dec;
     long long grid = 2LL * ctx->sm_count;
     if (grid > n_frames) grid = n_frames;
@@ -641,7 +653,7 @@ static int launch_decim(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64
         auto k = demod_decim_kernel<SFv, Tv, NBv>;                                                         \
         PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D.smem_bytes)); \
         k<<<(unsigned)grid, DEMOD_THREADS, D.smem_bytes, ctx->stream>>>(D, (const float2*)iq, audio, n_frames, \
-                                                                         (double*)pl->U_scratch);          \
+                                                                         (double*)pl->U_scratch, moments, mom_fpb); \
     } while (0)
     if (D.SF == 8) {
         if (D.T == 32 && D.nbuf == 2) DECIM_LAUNCH(8, 32, 2);
@@ -1044,6 +1056,15 @@ int pss_demod_c64_dev(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t
     if (n_frames == 0) return PSS_OK;
     if (pl->kind == PSS_PLAN_DECIM) return launch_decim(ctx, pl, iq, n_frames, audio);
     return launch_frame(ctx, pl, iq, n_frames, audio);
+}
+
+int pss_demod_c64_dev_moments(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t n_frames, float* audio,
+                              const double* moments, int frames_per_block) {
+    if (!ctx || !pl || !iq || !audio || n_frames < 0) return PSS_ERR_ARG;
+    if (moments && frames_per_block < 1) return PSS_ERR_ARG;
+    if (n_frames == 0) return PSS_OK;
+    if (pl->kind == PSS_PLAN_DECIM && pl->dec.SF == 16) return launch_decim(ctx, pl, iq, n_frames, audio, moments, frames_per_block);
+    return pss_demod_c64_dev(ctx, pl, iq, n_frames, audio);
 }
 
 int pss_demod_c64(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t n_frames, float* audio) {

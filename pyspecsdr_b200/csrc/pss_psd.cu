@@ -30,6 +30,7 @@ struct PsdParams {
     int use_abs;
     float thr;
     const void* ystage;   // second stage of a large transform: cx<T> rows [n_frames][N] (LOG2N1 > 0)
+    double* moments;      // [n_frames][4] sum I^2, Q^2, IQ of each frame (by-product for the WFM demod), or null
 };
 
 template <int LOG2N, typename T>
@@ -113,6 +114,7 @@ psd_kernel(const PsdParams p) {
     float* fscr = reinterpret_cast<float*>(dscr + 16);        // [32] per-warp max / min
     unsigned* uscr = reinterpret_cast<unsigned*>(fscr + 32);  // [16] select state
     static_assert(EPI == EPI_RAW || N >= 512, "epilogues need N >= 512");
+    __shared__ double mom_s[C::THREADS / 32][3];
 
     // ---- pass 0: global (coalesced 8-byte loads) * window -> radix-16 -> shared
     {
@@ -124,15 +126,36 @@ psd_kernel(const PsdParams p) {
         } else {
             const float2* src = p.iq + frame * N;
             const T* win = reinterpret_cast<const T*>(p.window);
+            float mii = 0.f, mqq = 0.f, miq = 0.f;
 #pragma unroll
             for (int r = 0; r < 16; ++r) {
                 const int idx = t + r * TPF;
                 const float2 s = live ? __ldg(src + idx) : make_float2(0.f, 0.f);
+                if constexpr (EPI == EPI_SMOOTH && N >= 512) {
+                    mii = fmaf(s.x, s.x, mii);
+                    mqq = fmaf(s.y, s.y, mqq);
+                    miq = fmaf(s.x, s.y, miq);
+                }
                 if (win) {
                     const T w = __ldg(win + idx);
                     v[r] = {(T)s.x * w, (T)s.y * w};
                 } else {
                     v[r] = {(T)s.x, (T)s.y};
+                }
+            }
+            if constexpr (EPI == EPI_SMOOTH && N >= 512) {
+                if (p.moments) {          // frame moments: float partials per warp, fp64 across the frame
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        mii += __shfl_xor_sync(0xffffffffu, mii, o);
+                        mqq += __shfl_xor_sync(0xffffffffu, mqq, o);
+                        miq += __shfl_xor_sync(0xffffffffu, miq, o);
+                    }
+                    if ((tid & 31) == 0) {
+                        mom_s[tid >> 5][0] = (double)mii;
+                        mom_s[tid >> 5][1] = (double)mqq;
+                        mom_s[tid >> 5][2] = (double)miq;
+                    }
                 }
             }
         }
@@ -142,6 +165,18 @@ psd_kernel(const PsdParams p) {
         for (int q = 0; q < 16; ++q) buf[fft_swz(base + fft_perm<16>(q))] = v[q];
     }
     __syncthreads();
+    if constexpr (EPI == EPI_SMOOTH && N >= 512 && LOG2N1 == 0) {
+        if (p.moments && live && t == 0) {
+            double a = 0.0, b = 0.0, c = 0.0;
+            for (int w = 0; w < TPF / 32; ++w) {
+                a += mom_s[f * (TPF / 32) + w][0];
+                b += mom_s[f * (TPF / 32) + w][1];
+                c += mom_s[f * (TPF / 32) + w][2];
+            }
+            double* m = p.moments + frame * 4;
+            m[0] = a; m[1] = b; m[2] = c; m[3] = 0.0;
+        }
+    }
 
     // ---- |X|^2 -> dB at the fft-shifted position
     auto emit = [&](int k, const cx<T> X) {
@@ -799,7 +834,8 @@ extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_f
         return PSS_ERR_ARG;
     if (precision != PSS_PREC_FP64 && precision != PSS_PREC_FP32) return PSS_ERR_ARG;
     if (epilogue == PSS_EPI_RAW && !out->db) return PSS_ERR_ARG;
-    if (epilogue == PSS_EPI_RAW && (out->cols || out->stats)) return PSS_ERR_UNSUPPORTED;
+    if (epilogue == PSS_EPI_RAW && (out->cols || out->stats || out->moments)) return PSS_ERR_UNSUPPORTED;
+    if (out->moments && N > 8192) return PSS_ERR_UNSUPPORTED;
     if (out->cols && out->W < 1) return PSS_ERR_ARG;
     const int log2n = ilog2_exact(N);
     if (log2n < 0) return PSS_ERR_UNSUPPORTED;
@@ -821,6 +857,7 @@ extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_f
     p.cols = out->cols;
     p.W = out->W;
     p.stats = out->stats;
+    p.moments = out->moments;
     if (fp32) return launch_by_n<float, EPI_RAW>(ctx, log2n, p);
     if (epilogue == PSS_EPI_RAW) return launch_by_n<double, EPI_RAW>(ctx, log2n, p);
     return launch_by_n<double, EPI_SMOOTH>(ctx, log2n, p);

@@ -111,3 +111,16 @@ def test_wfm_below_106k_raises_like_the_reference(ctx):
         O.demod(x, 48000.0, "WFM")
     with pytest.raises(ValueError):
         ctx.demod(x, 48000.0, "WFM")
+
+
+def test_wfm_with_psd_moments_matches_oracle(ctx):
+    """The main-loop fusion: the PSD kernel's per-frame I/Q moments feed the WFM demodulator, which then
+    skips its own iq_correction pass; audio must stay within tolerance (pipeline path)."""
+    fs, n = 2.4e6, 32768
+    x = np.stack([synth.make("wbfm", n, seed=70 + s) * np.complex64(0.9 + 0.05j) for s in range(5)]).astype(np.complex64)
+    out = ctx.pipeline(x, fs, "WFM", n_fft=4096, W=64)
+    alone = ctx.demod(x, fs, "WFM")
+    for f in range(len(x)):
+        ref = O.demod(x[f], fs, "WFM")
+        assert rms(out["audio"][f], ref) <= TOL_RMS
+        assert rms(out["audio"][f], alone[f].astype(np.float64)) <= 1e-6
