@@ -38,6 +38,7 @@ struct FrameDevFwd {
     const double* AC = nullptr;
     const double* ACB = nullptr;
     size_t smem_bytes = 0;
+    double coef[5][5] = {};     // b0 b1 b2 a1 a2 (a0-normalised) by value: kernel-parameter constants
 };
 
 struct pss_demod_plan {
@@ -745,7 +746,7 @@ demod_fir_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
 // the 2*n_sections-dimensional state over the chunks gives every chunk's true initial state, pass B
 // re-runs the chunk from it and emits the outputs.
 template <int NS>
-__device__ __forceinline__ double sos_step(const double (&c)[NS][5], double (&z)[NS][2], double v) {
+__device__ __forceinline__ double sos_step(const double (&c)[5][5], double (&z)[NS][2], double v) {
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
         const double y = fma(c[s][0], v, z[s][0]);                    // b0*x + z0
@@ -769,16 +770,8 @@ demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
     double* redd = XB + 1024;                             // [32]
     float* row = reinterpret_cast<float*>(redd + 32);     // [N + N/C] skewed: idx + idx / C
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double c[NS][5];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
-        const double a0 = D.sos[s * 6 + 3];
-        c[s][0] = D.sos[s * 6 + 0] / a0;
-        c[s][1] = D.sos[s * 6 + 1] / a0;
-        c[s][2] = D.sos[s * 6 + 2] / a0;
-        c[s][3] = D.sos[s * 6 + 4] / a0;
-        c[s][4] = D.sos[s * 6 + 5] / a0;
-    }
+    // the coefficients are read straight from the kernel-parameter constant bank (no registers)
+    const double (&c)[5][5] = D.coef;
     for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
         const float2* x = iq + frame * N;
         const float* xr = reinterpret_cast<const float*>(iq) + frame * N;
@@ -971,6 +964,14 @@ static int create_frame(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
         ACB = tmp;
     }
     if ((rc = upload(ctx, pl, d->sos, (size_t)ns * 6 * 8, &p))) return rc; F.sos = (const double*)p;
+    for (int s2 = 0; s2 < ns; ++s2) {
+        const double* cc = d->sos + s2 * 6;
+        F.coef[s2][0] = cc[0] / cc[3];
+        F.coef[s2][1] = cc[1] / cc[3];
+        F.coef[s2][2] = cc[2] / cc[3];
+        F.coef[s2][3] = cc[4] / cc[3];
+        F.coef[s2][4] = cc[5] / cc[3];
+    }
     if ((rc = upload(ctx, pl, AC.data(), 256 * 8, &p))) return rc; F.AC = (const double*)p;
     if ((rc = upload(ctx, pl, ACB.data(), 256 * 8, &p))) return rc; F.ACB = (const double*)p;
     F.smem_bytes = ((size_t)(FRAME_THREADS + 2) * 16 * 8 + 512 * 8 + 1024 * 8 + 32 * 8 + ((size_t)d->N + d->N / F.C + 8) * 4 + 15) & ~(size_t)15;
