@@ -42,7 +42,41 @@ struct PsdCfg {
     static constexpr int MINB = (sizeof(T) * 2 * N * FPC <= 32 * 1024) ? 4 : (sizeof(T) * 2 * N * FPC <= 64 * 1024) ? 2 : 1;
     static constexpr size_t SMEM = (size_t)FPC * N * sizeof(cx<T>);
     static constexpr int NP = pss_num_passes(LOG2N);
+    static constexpr int CAP = TPF < 64 ? TPF : 64;          // median candidates ranked directly (EPI_SMOOTH)
 };
+
+
+// Every warp scans a 256-bin shared histogram by itself (no broadcast barrier): finds the bin holding
+// the element of 0-based rank `rank`, returns the bin, its count and the rank within the bin.
+__device__ __forceinline__ void hist_pick(const unsigned* h, unsigned& rank, unsigned& digit, unsigned& count,
+                                          const int lane) {
+    const uint4 a = reinterpret_cast<const uint4*>(h)[2 * lane];
+    const uint4 b = reinterpret_cast<const uint4*>(h)[2 * lane + 1];
+    const unsigned c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    unsigned sum = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) sum += c[q];
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, incl > rank);
+    const int L = hit ? __ffs(hit) - 1 : 31;
+    unsigned r = rank - (incl - sum), dg = 7, cc = c[7];
+    bool found = false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (!found) {
+            if (r < c[q]) { dg = q; cc = c[q]; found = true; }
+            else if (q < 7) r -= c[q];
+        }
+    }
+    digit = __shfl_sync(0xffffffffu, 8u * lane + dg, L);
+    rank = __shfl_sync(0xffffffffu, r, L);
+    count = __shfl_sync(0xffffffffu, cc, L);
+}
 
 
 // One Stockham pass P >= 1 (shared -> registers -> shared, or -> `out` on the last pass).
@@ -109,11 +143,25 @@ psd_kernel(const PsdParams p) {
     // frame-local scratch that aliases the exchange buffer once the last pass has read it
     float* row = reinterpret_cast<float*>(buf);           // [N] dB, fft-shifted
     float* srow = row + N;                                // [N] smoothed / clamped
-    unsigned* hist = reinterpret_cast<unsigned*>(srow + N);   // [2][256]
-    double* dscr = reinterpret_cast<double*>(hist + 512);     // [16] per-warp sums
-    float* fscr = reinterpret_cast<float*>(dscr + 16);        // [32] per-warp max / min
-    unsigned* uscr = reinterpret_cast<unsigned*>(fscr + 32);  // [16] select state
+    unsigned* hist = reinterpret_cast<unsigned*>(srow + N);   // [2][256] (rare path: [4][256])
     static_assert(EPI == EPI_RAW || N >= 512, "epilogues need N >= 512");
+    constexpr bool SM = EPI == EPI_SMOOTH;
+    __shared__ unsigned us_s[SM ? C::FPC : 1][16];        // [0]=raw kmin [1]=raw kmax [2]=#cand [3]=min key above [4]=v1 [5]=v2 [6]=nan
+    __shared__ unsigned uf_s[SM ? C::FPC : 1][8];         // rare path: [0]=kmin [1]=kmax [2]=cnt_le [3]=min_gt
+    __shared__ float cand_s[SM ? C::FPC : 1][SM ? C::CAP : 1];
+    constexpr int FS = EPI == EPI_RAW ? 1 : C::FPC;
+    __shared__ double dscr_s[FS][16];                     // per-warp sums
+    __shared__ float fscr_s[FS][32];                      // per-warp max / min
+    __shared__ unsigned uscr_s[FS][16];                   // scanner partial counts
+    double* dscr = dscr_s[EPI == EPI_RAW ? 0 : f];
+    float* fscr = fscr_s[EPI == EPI_RAW ? 0 : f];
+    unsigned* uscr = uscr_s[EPI == EPI_RAW ? 0 : f];
+    if constexpr (SM) {
+        if (t < 16) us_s[f][t] = (t == 0 || t == 3) ? 0xffffffffu : 0u;
+        if (t < 8) uf_s[f][t] = (t == 0 || t == 3) ? 0xffffffffu : 0u;
+    }
+    float rmin = INFINITY, rmax = -INFINITY;              // EPI_SMOOTH: bounds / NaN flag of this thread's raw dB values
+    bool rnan = false;
     __shared__ double mom_s[C::THREADS / 32][3];
 
     // ---- pass 0: global (coalesced 8-byte loads) * window -> radix-16 -> shared
@@ -199,6 +247,11 @@ psd_kernel(const PsdParams p) {
             if (live) p.db[frame * N + pos] = d;
         } else {
             row[pos] = d;
+            if constexpr (EPI == EPI_SMOOTH) {
+                rmin = fminf(rmin, d);
+                rmax = fmaxf(rmax, d);
+                rnan |= d != d;
+            }
         }
     };
     if constexpr (NP == 2) {
@@ -245,165 +298,184 @@ psd_kernel(const PsdParams p) {
     }
 
     if constexpr (EPI == EPI_SMOOTH) {
+        // Thread t owns four groups of 4 consecutive bins, group q at 4*t + 4*TPF*q: float4 shared and
+        // global accesses with a 16-byte lane stride (conflict-free, fully coalesced).
         constexpr int n = N - 4;
+        constexpr int CAP = C::CAP;
         const int wf = t >> 5, lane = t & 31, nw = TPF / 32;
-        __syncthreads();                       // row complete
-        // 5-bin 'valid' moving average, 16 consecutive outputs per thread
+        unsigned* us = us_s[f];
+        float* cand = cand_s[f];
+        {   // bounds of the raw row (they bound every 5-bin mean), NaN flag; before the row barrier
+            const unsigned kmn = __reduce_min_sync(0xffffffffu, f2key(rmin));
+            const unsigned kmx = __reduce_max_sync(0xffffffffu, f2key(rmax));
+            if (lane == 0) {
+                atomicMin(&us[0], kmn);
+                atomicMax(&us[1], kmx);
+            }
+            if (__any_sync(0xffffffffu, rnan) && lane == 0) atomicOr(&us[6], 1u);
+        }
+        for (int b = t; b < 512; b += TPF) hist[b] = 0u;     // the exchange buffer is dead after the last pass
+        __syncthreads();                                     // B1: row complete, histograms clear, bounds known
         float s[16];
-        unsigned key[16];
-        const int i0 = t * 16;
+        unsigned b16[16];
+        bool gvalid[4];
         {
-            float d[20];
-            const float4* r4 = reinterpret_cast<const float4*>(row + i0);
+            const float lo = key2f(us[0]), hi = key2f(us[1]);
+            const float scale = hi > lo ? 65535.0f / (hi - lo) : 0.f;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 x = r4[q];
-                d[4 * q] = x.x; d[4 * q + 1] = x.y; d[4 * q + 2] = x.z; d[4 * q + 3] = x.w;
-            }
-            if (i0 + 16 < N) {
-                const float4 x = r4[4];
-                d[16] = x.x; d[17] = x.y; d[18] = x.z; d[19] = x.w;
-            } else {
-                d[16] = d[17] = d[18] = d[19] = 0.f;
-            }
+                const int i0 = 4 * t + 4 * TPF * q;
+                gvalid[q] = i0 < n;
+                const float4 a = *reinterpret_cast<const float4*>(row + i0);
+                const float4 c = i0 + 4 < N ? *reinterpret_cast<const float4*>(row + i0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float d[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
 #pragma unroll
-            for (int m = 0; m < 16; ++m)
-                s[m] = ((d[m] + d[m + 1]) + (d[m + 2] + d[m + 3]) + d[m + 4]) * 0.2f;
-        }
-        const int nvalid = min(16, n - i0);     // 16, or 12 for the last thread of the frame
-        unsigned kmin = 0xffffffffu, kmax = 0u;
-        bool has_nan = false;
-#pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            key[m] = f2key(s[m]);
-            if (m < nvalid) {
-                kmin = min(kmin, key[m]);
-                kmax = max(kmax, key[m]);
-                has_nan |= (s[m] != s[m]);
-            }
-        }
-        if (t < 16) uscr[t] = (t == 0 || t == 5) ? 0xffffffffu : 0u;   // [0]=min [1]=max [4]=cnt_le [5]=min_gt [6]=nan
-        for (int b = t; b < 512; b += TPF) hist[b] = 0u;
-        __syncthreads();
-        kmin = __reduce_min_sync(0xffffffffu, kmin);
-        kmax = __reduce_max_sync(0xffffffffu, kmax);
-        if (lane == 0) {
-            atomicMin(&uscr[0], kmin);
-            atomicMax(&uscr[1], kmax);
-        }
-        if (__any_sync(0xffffffffu, has_nan) && lane == 0) atomicOr(&uscr[6], 1u);
-        __syncthreads();
-        kmin = uscr[0];
-        kmax = uscr[1];
-        const int common = min(__clz((int)(kmin ^ kmax)), 31);
-        // normalised keys: order preserved, leading bits spread over the occupied range
-#pragma unroll
-        for (int m = 0; m < 16; ++m) key[m] = (key[m] - kmin) << common;
-        // radix select of rank (n-1)/2, four 8-bit digits
-        unsigned rank = (unsigned)((n - 1) / 2), prefix = 0u;
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-            const int shift = 24 - 8 * ps;
-            unsigned* h = hist + (ps & 1) * 256;
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const bool match = ps == 0 ? true : (key[m] >> (shift + 8)) == prefix;
-                if (m < nvalid && match) atomicAdd(&h[(key[m] >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (wf == 0) {
-                const uint4 a = reinterpret_cast<const uint4*>(h)[2 * lane];
-                const uint4 b = reinterpret_cast<const uint4*>(h)[2 * lane + 1];
-                const unsigned c[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-                unsigned sum = 0;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) sum += c[q];
-                unsigned incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += up;
+                for (int e = 0; e < 4; ++e) {
+                    const float v = ((d[e] + d[e + 1]) + (d[e + 2] + d[e + 3]) + d[e + 4]) * 0.2f;
+                    s[4 * q + e] = v;
+                    // monotone 16-bit bucket over the occupied dB range (NaN and negatives convert to 0)
+                    b16[4 * q + e] = min(65535u, __float2uint_rz((v - lo) * scale));
                 }
-                const unsigned hit = __ballot_sync(0xffffffffu, incl > rank);
-                const int L = __ffs(hit) - 1;
-                if (lane == L) {
-                    unsigned r = rank - (incl - sum);
-                    int dg = 0;
-                    bool found = false;
+            }
+        }
+        // exact lower/upper median: two 8-bit histogram levels over the linear buckets, then the few
+        // elements of the selected bucket are ranked directly (flat rows fall back to a key radix select)
+        unsigned rank = (unsigned)((n - 1) / 2), d0, d1, m;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (!found) {
-                            if (r < c[q]) { dg = q; found = true; }
-                            else r -= c[q];
-                        }
-                    }
-                    uscr[2] = (unsigned)(8 * lane + dg);
-                    uscr[3] = r;
-                }
-            } else {
-                unsigned* hn = hist + ((ps + 1) & 1) * 256;      // clear the other histogram
-                for (int b = t - 32; b < 256; b += TPF - 32) hn[b] = 0u;
-            }
-            if (TPF == 32) {                                     // single-warp frame: clear here
-                unsigned* hn = hist + ((ps + 1) & 1) * 256;
-                __syncwarp();
-                for (int b = t; b < 256; b += 32) hn[b] = 0u;
-            }
-            __syncthreads();
-            prefix = (prefix << 8) | uscr[2];
-            rank = uscr[3];
-        }
-        const unsigned key1n = prefix;                          // normalised key of the lower median
-        unsigned cnt_le = 0, min_gt = 0xffffffffu;
+        for (int q = 0; q < 4; ++q)
+            if (gvalid[q]) {
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            if (m < nvalid) {
-                cnt_le += key[m] <= key1n;
-                if (key[m] > key1n) min_gt = min(min_gt, key[m]);
+                for (int e = 0; e < 4; ++e) atomicAdd(&hist[b16[4 * q + e] >> 8], 1u);
             }
-        }
-        cnt_le = __reduce_add_sync(0xffffffffu, cnt_le);
-        min_gt = __reduce_min_sync(0xffffffffu, min_gt);
-        if (lane == 0) {
-            atomicAdd(&uscr[4], cnt_le);
-            atomicMin(&uscr[5], min_gt);
-        }
-        __syncthreads();
-        float thr;
+        __syncthreads();                                     // B2
+        hist_pick(hist, rank, d0, m, lane);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (gvalid[q]) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if ((b16[4 * q + e] >> 8) == d0) atomicAdd(&hist[256 + (b16[4 * q + e] & 255u)], 1u);
+            }
+        __syncthreads();                                     // B3
+        hist_pick(hist + 256, rank, d1, m, lane);
+        const unsigned sel = (d0 << 8) | d1;
+        const bool flat = m > (unsigned)CAP;
         {
-            const unsigned key2n = ((n & 1) || uscr[4] > (unsigned)(n / 2)) ? key1n : uscr[5];
-            const float v1 = key2f((key1n >> common) + kmin);
-            const float v2 = key2f((key2n >> common) + kmin);
-            thr = (float)(0.5 * ((double)v1 + (double)v2) - 10.0);
-            if (uscr[6]) thr = __int_as_float(0x7fc00000);       // np.median propagates NaN
+            unsigned kgt = 0xffffffffu;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (gvalid[q]) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const unsigned b = b16[4 * q + e];
+                        if (b == sel && !flat) {
+                            const unsigned slot = atomicAdd(&us[2], 1u);
+                            if (slot < (unsigned)CAP) cand[slot] = s[4 * q + e];
+                        }
+                        if (b > sel) kgt = min(kgt, f2key(s[4 * q + e]));
+                    }
+                }
+            kgt = __reduce_min_sync(0xffffffffu, kgt);
+            if (lane == 0 && kgt != 0xffffffffu) atomicMin(&us[3], kgt);
         }
+        float v1, v2;
+        if (!__syncthreads_or(flat)) {                       // B4
+            if ((unsigned)t < m) {
+                const float c = cand[t];
+                unsigned rk = 0;
+                for (unsigned j = 0; j < m; ++j) {
+                    const float o = cand[j];
+                    rk += (o < c) || (o == c && j < (unsigned)t);
+                }
+                if (rk == rank) us[4] = __float_as_uint(c);
+                if (rk == rank + 1u) us[5] = __float_as_uint(c);
+            }
+            __syncthreads();                                 // B5
+            v1 = __uint_as_float(us[4]);
+            v2 = (n & 1) ? v1 : (rank + 1u < m ? __uint_as_float(us[5]) : key2f(us[3]));
+        } else {
+            // ---- rare path (a frame of this CTA has > CAP equal-bucket elements): 4 x 8-bit radix select
+            // on order-preserving keys normalised to the occupied key range; every frame of the CTA runs it
+            unsigned* uf = uf_s[f];
+            unsigned key[16];
+            unsigned kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+            for (int m2 = 0; m2 < 16; ++m2) {
+                key[m2] = f2key(s[m2]);
+                if (gvalid[m2 >> 2]) {
+                    kmin = min(kmin, key[m2]);
+                    kmax = max(kmax, key[m2]);
+                }
+            }
+            for (int b = t; b < 1024; b += TPF) hist[b] = 0u;
+            kmin = __reduce_min_sync(0xffffffffu, kmin);
+            kmax = __reduce_max_sync(0xffffffffu, kmax);
+            if (lane == 0) {
+                atomicMin(&uf[0], kmin);
+                atomicMax(&uf[1], kmax);
+            }
+            __syncthreads();
+            kmin = uf[0];
+            kmax = uf[1];
+            const int common = min(__clz((int)(kmin ^ kmax)), 31);
+#pragma unroll
+            for (int m2 = 0; m2 < 16; ++m2) key[m2] = (key[m2] - kmin) << common;
+            unsigned rk = (unsigned)((n - 1) / 2), prefix = 0u, dg, cnt;
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                const int shift = 24 - 8 * ps;
+                unsigned* h = hist + ps * 256;
+#pragma unroll
+                for (int m2 = 0; m2 < 16; ++m2) {
+                    const bool match = ps == 0 ? true : (key[m2] >> (shift + 8)) == prefix;
+                    if (gvalid[m2 >> 2] && match) atomicAdd(&h[(key[m2] >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                hist_pick(h, rk, dg, cnt, lane);
+                prefix = (prefix << 8) | dg;
+            }
+            const unsigned key1n = prefix;                   // normalised key of the lower median
+            unsigned cnt_le = 0, min_gt = 0xffffffffu;
+#pragma unroll
+            for (int m2 = 0; m2 < 16; ++m2) {
+                if (gvalid[m2 >> 2]) {
+                    cnt_le += key[m2] <= key1n;
+                    if (key[m2] > key1n) min_gt = min(min_gt, key[m2]);
+                }
+            }
+            cnt_le = __reduce_add_sync(0xffffffffu, cnt_le);
+            min_gt = __reduce_min_sync(0xffffffffu, min_gt);
+            if (lane == 0) {
+                atomicAdd(&uf[2], cnt_le);
+                atomicMin(&uf[3], min_gt);
+            }
+            __syncthreads();
+            const unsigned key2n = ((n & 1) || uf[2] > (unsigned)(n / 2)) ? key1n : uf[3];
+            v1 = key2f((key1n >> common) + kmin);
+            v2 = key2f((key2n >> common) + kmin);
+        }
+        float thr = (float)(0.5 * ((double)v1 + (double)v2) - 10.0);
+        const bool any_nan = us[6] != 0u;
+        if (any_nan) thr = __int_as_float(0x7fc00000);       // np.median propagates NaN
         // clamp, row statistics, store
         float mx = -INFINITY, mn = INFINITY, fsum = 0.f;
 #pragma unroll
-        for (int m = 0; m < 16; ++m) {
-            if (s[m] < thr) s[m] = thr;
-            if (m < nvalid) {
-                mx = fmaxf(mx, s[m]);
-                mn = fminf(mn, s[m]);
-                fsum += s[m];
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float v = s[4 * q + e];
+                if (v < thr) v = thr;
+                s[4 * q + e] = v;
+                if (gvalid[q]) {
+                    mx = fmaxf(mx, v);
+                    mn = fminf(mn, v);
+                    fsum += v;
+                }
             }
-        }
-        {
-            float4* o4 = reinterpret_cast<float4*>(srow + i0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) o4[q] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
-        }
-        if (live && p.db) {
-            float* dst = p.db + frame * n + i0;
-            if (nvalid == 16) {
-                float4* o4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) o4[q] = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
-            } else {
-#pragma unroll
-                for (int m = 0; m < 16; ++m)
-                    if (m < nvalid) dst[m] = s[m];
-            }
+            const int i0 = 4 * t + 4 * TPF * q;
+            const float4 o = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+            *reinterpret_cast<float4*>(srow + i0) = o;
+            if (live && p.db && gvalid[q]) *reinterpret_cast<float4*>(p.db + frame * n + i0) = o;
         }
         mx = warp_max(mx);
         mn = warp_min(mn);
@@ -413,7 +485,7 @@ psd_kernel(const PsdParams p) {
             fscr[16 + wf] = mn;
             dscr[wf] = dsum;
         }
-        __syncthreads();
+        __syncthreads();                                     // B6: clamped row + warp partials visible
         if (live && p.stats && t == 0) {
             float a = fscr[0], b = fscr[16];
             double sm = dscr[0];
@@ -424,8 +496,8 @@ psd_kernel(const PsdParams p) {
             }
             const float nanv = __int_as_float(0x7fc00000);
             float4 st;
-            st.x = uscr[6] ? nanv : a;                    // np.max
-            st.y = uscr[6] ? nanv : (float)(sm / n);      // np.mean
+            st.x = any_nan ? nanv : a;                    // np.max
+            st.y = any_nan ? nanv : (float)(sm / n);      // np.mean
             st.z = b;                                     // finite min
             st.w = a;                                     // finite max
             reinterpret_cast<float4*>(p.stats)[frame] = st;
