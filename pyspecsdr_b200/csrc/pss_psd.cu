@@ -80,9 +80,19 @@ __device__ __forceinline__ void hist_pick(const unsigned* h, unsigned& rank, uns
 
 
 // One Stockham pass P >= 1 (shared -> registers -> shared, or -> `out` on the last pass).
-template <int LOG2N, int P, typename T, typename OutF>
+struct CtaBarrier {
+    __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+// Named barrier over one 256-thread half of a 512-thread CTA (ids 1 and 2), so the two halves run
+// their row transforms out of phase like two independent CTAs would.
+struct HalfBarrier {
+    int id;
+    __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
+};
+
+template <int LOG2N, int P, typename T, typename OutF, typename Bar = CtaBarrier>
 __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<T>* __restrict__ wpre,
-                                              const int t, OutF&& out) {
+                                              const int t, OutF&& out, Bar bar = Bar()) {
     constexpr int N = 1 << LOG2N, TPF = N / 16;
     constexpr int BITS = pss_pass_bits(LOG2N, P), R = 1 << BITS, NS = 1 << (4 * P);
     constexpr int TI = N / R, ITEMS = 16 / R, NP = pss_num_passes(LOG2N);
@@ -91,7 +101,7 @@ __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<
     for (int it = 0; it < ITEMS; ++it)
 #pragma unroll
         for (int r = 0; r < R; ++r) v[it * R + r] = buf[fft_swz(t + it * TPF + r * TI)];
-    __syncthreads();
+    bar();
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
         const int j = t + it * TPF;
@@ -108,7 +118,7 @@ __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<
                 buf[fft_swz(idx)] = v[it * R + p];
         }
     }
-    if constexpr (P != NP - 1) __syncthreads();
+    if constexpr (P != NP - 1) bar();
 }
 
 // LOG2N1 > 0: this launch is the second stage of a length N*2^LOG2N1 transform (four-step FFT): frame
@@ -714,6 +724,215 @@ row_epilogue_kernel(const float* __restrict__ raw, const int N, const long long 
     }
 }
 
+// ---------------------------------------------------------------------------------- fused large transforms
+// N = N1 * 4096 (N1 = 4, 8, 16: 16384 ... 65536 points; the app's default read is 32768 samples,
+// pyspecsdr.py:105,2236) in ONE persistent launch, one frame per CTA at a time (512 threads, 1 CTA/SM):
+//   stage A: per column n2, window, N1-point DFT over the stride-4096 samples in registers, twiddle
+//            W_N^(n2*k1), fp64 rows Y[k1][n2] to this CTA's private scratch (reused every frame, so it
+//            lives in L2; HBM sees the 8-byte samples once and the 4-byte dB once);
+//   stage B: the two 256-thread halves of the CTA each run 4096-point row transforms (radix-16
+//            Stockham through their own 64 KB of shared memory, named barriers, out of phase like
+//            two CTAs) and scatter bins k1 + N1*k2 as dB;
+//   epilogue (EPI_SMOOTH): the raw dB row comes back from L2, the smoothed row is kept in the
+//            128 KB of shared memory the transforms no longer need (N <= 32768) and the exact
+//            median / clamp / statistics / resample run on it.
+// L2 residency control for the fused large transforms: the per-CTA scratch (fp64 rows, raw dB row) is
+// written and read back within one frame period and must survive the 1 GB/ms input stream flowing
+// through the same L2, so scratch accesses carry an evict_last policy and the stream is read evict-first.
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_keep(double2* p, const double x, const double y, const unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(x), "d"(y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_keep(float* p, const float v, const unsigned long long pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ double2 ld_keep(const double2* p, const unsigned long long pol) {
+    double2 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+__device__ __forceinline__ float4 ld_keep(const float4* p, const unsigned long long pol) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol) : "memory");
+    return v;
+}
+
+struct PsdLargeParams {
+    const float2* iq;
+    const double* window;          // [N] or nullptr
+    const cx<double>* twN;         // [4096]: W_N^n2
+    const cx<double>* tw;          // row-transform base twiddles (4096-point tables)
+    long long n_frames;
+    float* db;
+    float* cols;
+    int W;
+    float* stats;
+    cx<double>* Y;                 // [grid][N] scratch
+    float* rawdb;                  // [grid][N] scratch (EPI_SMOOTH)
+    float* srow2;                  // [grid][N] scratch (EPI_SMOOTH, rows that do not fit shared memory)
+};
+
+template <int LOG2N, int EPI>
+__global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams p) {
+    constexpr int N = 1 << LOG2N, LOG2N1 = LOG2N - 12, N1 = 1 << LOG2N1, N2 = 4096, n = N - 4;
+    constexpr bool SROW_SMEM = (size_t)N * 4 <= 2 * N2 * sizeof(cx<double>);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned hist[256];
+    __shared__ unsigned us[8];
+    __shared__ double dsum_s[16];
+    __shared__ float fmx_s[16], fmn_s[16];
+    const int tid = threadIdx.x, g = tid >> 8, t = tid & 255, lane = tid & 31, warp = tid >> 5;
+    cx<double>* buf = reinterpret_cast<cx<double>*>(smem_raw) + (size_t)g * N2;
+    const HalfBarrier hbar{1 + g};
+    cx<double> wpre[2];
+    wpre[0] = p.tw[t & 15];                       // pass 1: ns = 16, offset 0
+    wpre[1] = p.tw[16 + t];                       // pass 2: ns = 256, offset (256-16)/15 = 16
+    cx<double>* Y = p.Y + (size_t)blockIdx.x * N;
+    float* raw = EPI == EPI_SMOOTH ? p.rawdb + (size_t)blockIdx.x * N : nullptr;
+    const unsigned long long keep = l2_evict_last_policy();
+
+    for (long long frame = blockIdx.x; frame < p.n_frames; frame += gridDim.x) {
+        // ---- stage A: column DFTs
+        const float2* src = p.iq + frame * N;
+#pragma unroll(N1 == 4 ? 4 : N1 == 8 ? 2 : 1)
+        for (int c = 0; c < N2 / 512; ++c) {
+            const int n2 = tid + 512 * c;
+            cx<double> v[N1];
+#pragma unroll
+            for (int n1 = 0; n1 < N1; ++n1) {
+                const float2 s = __ldcs(src + n2 + N2 * n1);
+                if (p.window) {
+                    const double w = __ldg(p.window + n2 + N2 * n1);
+                    v[n1] = {(double)s.x * w, (double)s.y * w};
+                } else {
+                    v[n1] = {(double)s.x, (double)s.y};
+                }
+            }
+            fft_regs<N1, double>::run(v);
+            cx<double> o[N1];
+#pragma unroll
+            for (int q = 0; q < N1; ++q) o[fft_perm<N1>(q)] = v[q];
+            const double2 wn = __ldg(reinterpret_cast<const double2*>(p.twN + n2));
+            twiddle_apply<N1, double>(o, cx<double>{wn.x, wn.y});     // o[k1] *= W_N^(n2*k1)
+#pragma unroll
+            for (int k1 = 0; k1 < N1; ++k1)
+                st_keep(reinterpret_cast<double2*>(Y + k1 * N2 + n2), o[k1].x, o[k1].y, keep);
+        }
+        __syncthreads();
+        // ---- stage B: row transforms, two rows at a time
+        for (int pair = 0; pair < N1 / 2; ++pair) {
+            const int k1 = 2 * pair + g;
+            {
+                const double2* rowY = reinterpret_cast<const double2*>(Y + k1 * N2);
+                cx<double> v[16];
+#pragma unroll
+                for (int r = 0; r < 16; ++r) {
+                    const double2 y = ld_keep(rowY + t + r * 256, keep);
+                    v[r] = {y.x, y.y};
+                }
+                fft_regs<16, double>::run(v);
+                const int base = t << 4;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) buf[fft_swz(base + fft_perm<16>(q))] = v[q];
+            }
+            hbar();
+            auto emit = [&](int k, const cx<double> X) {
+                const float d = db_from_power(X.x * X.x + (X.y * X.y + 1e-10));
+                const int pos = (k1 + (k << LOG2N1)) ^ (N >> 1);
+                if constexpr (EPI == EPI_RAW) p.db[frame * N + pos] = d;
+                else st_keep(raw + pos, d, keep);
+            };
+            stockham_pass<12, 1, double>(buf, &wpre[0], t, [](int, cx<double>) {}, hbar);
+            stockham_pass<12, 2, double>(buf, &wpre[1], t, emit, hbar);
+        }
+        __syncthreads();
+        if constexpr (EPI == EPI_SMOOTH) {
+            float* srow = SROW_SMEM ? reinterpret_cast<float*>(smem_raw) : p.srow2 + (size_t)blockIdx.x * N;
+            bool has_nan = false;
+            for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
+                const float4 a = ld_keep(reinterpret_cast<const float4*>(raw + i0), keep);
+                const float4 c = ld_keep(reinterpret_cast<const float4*>(raw + i0 + 4), keep);     // i0 + 4 <= N - 4
+                const float d[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+                float sv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    sv[e] = ((d[e] + d[e + 1]) + (d[e + 2] + d[e + 3]) + d[e + 4]) * 0.2f;
+                    has_nan |= sv[e] != sv[e];
+                }
+                *reinterpret_cast<float4*>(srow + i0) = make_float4(sv[0], sv[1], sv[2], sv[3]);
+            }
+            const bool any_nan = __syncthreads_or(has_nan);
+            unsigned ka, kb;
+            row_select2_512(srow, n, (unsigned)((n - 1) / 2), hist, us, ka, kb);
+            float thr = (float)(0.5 * ((double)key2f(ka) + (double)key2f((n & 1) ? ka : kb)) - 10.0);
+            if (any_nan) thr = __int_as_float(0x7fc00000);
+            float mx = -INFINITY, mn = INFINITY;
+            double sm = 0.0;
+            float* dst = p.db ? p.db + frame * n : nullptr;
+            for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
+                float4 v = *reinterpret_cast<const float4*>(srow + i0);
+                v.x = v.x < thr ? thr : v.x;
+                v.y = v.y < thr ? thr : v.y;
+                v.z = v.z < thr ? thr : v.z;
+                v.w = v.w < thr ? thr : v.w;
+                mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w)));
+                mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+                sm += (double)((v.x + v.y) + (v.z + v.w));
+                *reinterpret_cast<float4*>(srow + i0) = v;
+                if (dst) __stcs(reinterpret_cast<float4*>(dst + i0), v);
+            }
+            mx = warp_max(mx);
+            mn = warp_min(mn);
+            sm = warp_sum(sm);
+            if (lane == 0) {
+                fmx_s[warp] = mx;
+                fmn_s[warp] = mn;
+                dsum_s[warp] = sm;
+            }
+            __syncthreads();
+            if (p.stats && tid == 0) {
+                float a = fmx_s[0], b = fmn_s[0];
+                double tt = dsum_s[0];
+                for (int w = 1; w < 16; ++w) {
+                    a = fmaxf(a, fmx_s[w]);
+                    b = fminf(b, fmn_s[w]);
+                    tt += dsum_s[w];
+                }
+                const float nanv = __int_as_float(0x7fc00000);
+                float4 st;
+                st.x = any_nan ? nanv : a;
+                st.y = any_nan ? nanv : (float)(tt / n);
+                st.z = b;
+                st.w = a;
+                reinterpret_cast<float4*>(p.stats)[frame] = st;
+            }
+            if (p.cols) {
+                const int W = p.W;
+                const double step = W > 1 ? (double)(n - 1) / (double)(W - 1) : 0.0;
+                for (int c = tid; c < W; c += 512) {
+                    const double x = (c == W - 1 && W > 1) ? (double)(n - 1) : c * step;
+                    const int j = (int)x;
+                    float o;
+                    if (j >= n - 1) {
+                        o = srow[n - 1];
+                    } else {
+                        const double y0 = srow[j], y1 = srow[j + 1];
+                        o = (float)((y1 - y0) * (x - (double)j) + y0);
+                    }
+                    p.cols[frame * W + c] = o;
+                }
+            }
+            __syncthreads();          // srow (shared) is the next frame's exchange buffer
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------- host side
 template <typename T>
 static int build_tables(pss_ctx* ctx, int log2n, pss_fft_tables& tab) {
@@ -821,6 +1040,17 @@ static int launch_stage_b(pss_ctx* ctx, const PsdParams& p) {
     return PSS_OK;
 }
 
+
+template <int LOG2N, int EPI>
+static int launch_large_fused(pss_ctx* ctx, const PsdLargeParams& p, unsigned grid) {
+    auto kern = psd_large_kernel<LOG2N, EPI>;
+    constexpr int SMEM = 2 * 4096 * (int)sizeof(cx<double>);
+    PSS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    kern<<<grid, 512, SMEM, ctx->stream>>>(p);
+    PSS_LAUNCH_CHECK(ctx);
+    return PSS_OK;
+}
+
 static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames, int window, int epilogue,
                      const pss_psd_out* out) {
     const int log2n2 = log2n == 17 ? 13 : 12;
@@ -848,6 +1078,35 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
             PSS_CUDA(ctx, cudaMemcpy(lt.window[kind], w.data(), N * sizeof(double), cudaMemcpyHostToDevice));
         }
     }
+    if (log2n <= 16) {
+        // fused persistent kernel: per-CTA scratch only (grid * N * 16 bytes of fp64 rows + the raw dB row)
+        const bool smooth = epilogue == PSS_EPI_SMOOTH_CLAMP;
+        const unsigned grid = (unsigned)(n_frames < ctx->sm_count ? n_frames : ctx->sm_count);
+        if ((rc = pss_reserve(ctx, &ctx->p_buf[7], &ctx->p_bytes[7], (size_t)grid * N * 16))) return rc;
+        PsdLargeParams lp{};
+        lp.iq = reinterpret_cast<const float2*>(iq);
+        lp.window = window == PSS_WINDOW_NONE ? nullptr : (const double*)lt.window[window];
+        lp.twN = (const cx<double>*)lt.twN;
+        lp.tw = (const cx<double>*)tab2->twiddle;
+        lp.n_frames = n_frames;
+        lp.db = out->db;
+        lp.cols = out->cols;
+        lp.W = out->W;
+        lp.stats = out->stats;
+        lp.Y = (cx<double>*)ctx->p_buf[7];
+        if (smooth) {
+            if ((rc = pss_reserve(ctx, &ctx->p_buf[9], &ctx->p_bytes[9], (size_t)grid * N * 4))) return rc;
+            lp.rawdb = (float*)ctx->p_buf[9];
+            if (log2n == 16) {
+                if ((rc = pss_reserve(ctx, &ctx->p_buf[8], &ctx->p_bytes[8], (size_t)grid * N * 4))) return rc;
+                lp.srow2 = (float*)ctx->p_buf[8];
+            }
+        }
+        if (log2n == 14) return smooth ? launch_large_fused<14, EPI_SMOOTH>(ctx, lp, grid) : launch_large_fused<14, EPI_RAW>(ctx, lp, grid);
+        if (log2n == 15) return smooth ? launch_large_fused<15, EPI_SMOOTH>(ctx, lp, grid) : launch_large_fused<15, EPI_RAW>(ctx, lp, grid);
+        return smooth ? launch_large_fused<16, EPI_SMOOTH>(ctx, lp, grid) : launch_large_fused<16, EPI_RAW>(ctx, lp, grid);
+    }
+    // 131072 points: three launches per L2-sized sub-batch.
     // scratch: fp64 rows of a sub-batch (kept <= 64 MB so it lives in L2) and, with an epilogue, the raw rows
     long long sub = (64LL << 20) / (N * 16);
     if (sub < 1) sub = 1;
