@@ -736,6 +736,74 @@ row_epilogue_kernel(const float* __restrict__ raw, const int N, const long long 
 //   epilogue (EPI_SMOOTH): the raw dB row comes back from L2, the smoothed row is kept in the
 //            128 KB of shared memory the transforms no longer need (N <= 32768) and the exact
 //            median / clamp / statistics / resample run on it.
+// Exact lower/upper median of a row of n floats (shared or L2-resident), all 512 threads of the CTA:
+// two 8-bit histogram levels over 65536 linear buckets of [lo, hi] (any bounds of the row), then the
+// few elements of the selected bucket are ranked directly.  Returns false (CTA-uniform) when the bucket
+// holds more than 64 elements (flat rows); the caller then runs the key radix select.
+// hist [512], us [8] ([2] = 0, [3] = 0xffffffff on entry), cand [64] are shared scratch.
+__device__ __forceinline__ bool row_median2_512(const float* __restrict__ srow, const int n, const float lo,
+                                                const float hi, unsigned* hist, unsigned* us, float* cand,
+                                                float& v1, float& v2) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const float scale = hi > lo ? 65535.0f / (hi - lo) : 0.f;
+    hist[tid] = 0u;
+    __syncthreads();
+    for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
+        const float4 v = *reinterpret_cast<const float4*>(srow + i0);
+        atomicAdd(&hist[min(65535u, __float2uint_rz((v.x - lo) * scale)) >> 8], 1u);
+        atomicAdd(&hist[min(65535u, __float2uint_rz((v.y - lo) * scale)) >> 8], 1u);
+        atomicAdd(&hist[min(65535u, __float2uint_rz((v.z - lo) * scale)) >> 8], 1u);
+        atomicAdd(&hist[min(65535u, __float2uint_rz((v.w - lo) * scale)) >> 8], 1u);
+    }
+    __syncthreads();
+    unsigned rank = (unsigned)((n - 1) / 2), d0, d1, m;
+    hist_pick(hist, rank, d0, m, lane);
+    for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
+        const float4 v = *reinterpret_cast<const float4*>(srow + i0);
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned b = min(65535u, __float2uint_rz((e[q] - lo) * scale));
+            if ((b >> 8) == d0) atomicAdd(&hist[256 + (b & 255u)], 1u);
+        }
+    }
+    __syncthreads();
+    hist_pick(hist + 256, rank, d1, m, lane);
+    if (m > 64u) return false;
+    const unsigned sel = (d0 << 8) | d1;
+    unsigned kgt = 0xffffffffu;
+    for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
+        const float4 v = *reinterpret_cast<const float4*>(srow + i0);
+        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const unsigned b = min(65535u, __float2uint_rz((e[q] - lo) * scale));
+            if (b == sel) {
+                const unsigned slot = atomicAdd(&us[2], 1u);
+                if (slot < 64u) cand[slot] = e[q];
+            }
+            if (b > sel) kgt = min(kgt, f2key(e[q]));
+        }
+    }
+    kgt = __reduce_min_sync(0xffffffffu, kgt);
+    if (lane == 0 && kgt != 0xffffffffu) atomicMin(&us[3], kgt);
+    __syncthreads();
+    if ((unsigned)tid < m) {
+        const float c = cand[tid];
+        unsigned rk = 0;
+        for (unsigned j = 0; j < m; ++j) {
+            const float o = cand[j];
+            rk += (o < c) || (o == c && j < (unsigned)tid);
+        }
+        if (rk == rank) us[4] = __float_as_uint(c);
+        if (rk == rank + 1u) us[5] = __float_as_uint(c);
+    }
+    __syncthreads();
+    v1 = __uint_as_float(us[4]);
+    v2 = (n & 1) ? v1 : (rank + 1u < m ? __uint_as_float(us[5]) : key2f(us[3]));
+    return true;
+}
+
 // L2 residency control for the fused large transforms: the per-CTA scratch (fp64 rows, raw dB row) is
 // written and read back within one frame period and must survive the 1 GB/ms input stream flowing
 // through the same L2, so scratch accesses carry an evict_last policy and the stream is read evict-first.
@@ -783,8 +851,9 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
     constexpr int N = 1 << LOG2N, LOG2N1 = LOG2N - 12, N1 = 1 << LOG2N1, N2 = 4096, n = N - 4;
     constexpr bool SROW_SMEM = (size_t)N * 4 <= 2 * N2 * sizeof(cx<double>);
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned hist[256];
-    __shared__ unsigned us[8];
+    __shared__ unsigned hist[512];
+    __shared__ unsigned us[8], ub[2];
+    __shared__ float cand[64];
     __shared__ double dsum_s[16];
     __shared__ float fmx_s[16], fmn_s[16];
     const int tid = threadIdx.x, g = tid >> 8, t = tid & 255, lane = tid & 31, warp = tid >> 5;
@@ -799,6 +868,10 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
 
     for (long long frame = blockIdx.x; frame < p.n_frames; frame += gridDim.x) {
         // ---- stage A: column DFTs
+        if constexpr (EPI == EPI_SMOOTH) {
+            if (tid < 8) us[tid] = tid == 3 ? 0xffffffffu : 0u;
+            if (tid < 2) ub[tid] = tid == 0 ? 0xffffffffu : 0u;      // raw-row bounds (keys)
+        }
         const float2* src = p.iq + frame * N;
 #pragma unroll(N1 == 4 ? 4 : N1 == 8 ? 2 : 1)
         for (int c = 0; c < N2 / 512; ++c) {
@@ -825,6 +898,15 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
                 st_keep(reinterpret_cast<double2*>(Y + k1 * N2 + n2), o[k1].x, o[k1].y, keep);
         }
         __syncthreads();
+        if constexpr (LOG2N == 14) {
+            // pull the next frame of this CTA into L2 while the row transforms keep the fp64 pipe busy
+            // (measured: -4 % at 16384 points; at 32768+ the scratch already fills the L2 and it hurts)
+            const long long nf = frame + gridDim.x;
+            if (nf < p.n_frames) {
+                const char* nx = reinterpret_cast<const char*>(p.iq + nf * N);
+                for (int l = tid; l < N * 8 / 128; l += 512) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)l * 128));
+            }
+        }
         // ---- stage B: row transforms, two rows at a time
         for (int pair = 0; pair < N1 / 2; ++pair) {
             const int k1 = 2 * pair + g;
@@ -855,11 +937,17 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
         if constexpr (EPI == EPI_SMOOTH) {
             float* srow = SROW_SMEM ? reinterpret_cast<float*>(smem_raw) : p.srow2 + (size_t)blockIdx.x * N;
             bool has_nan = false;
+            float rlo = INFINITY, rhi = -INFINITY;
             for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
                 const float4 a = ld_keep(reinterpret_cast<const float4*>(raw + i0), keep);
                 const float4 c = ld_keep(reinterpret_cast<const float4*>(raw + i0 + 4), keep);     // i0 + 4 <= N - 4
                 const float d[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
                 float sv[4];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    rlo = fminf(rlo, d[e]);
+                    rhi = fmaxf(rhi, d[e]);
+                }
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     sv[e] = ((d[e] + d[e + 1]) + (d[e + 2] + d[e + 3]) + d[e + 4]) * 0.2f;
@@ -867,10 +955,23 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
                 }
                 *reinterpret_cast<float4*>(srow + i0) = make_float4(sv[0], sv[1], sv[2], sv[3]);
             }
+            {
+                const unsigned klo = __reduce_min_sync(0xffffffffu, f2key(rlo));
+                const unsigned khi = __reduce_max_sync(0xffffffffu, f2key(rhi));
+                if (lane == 0) {
+                    atomicMin(&ub[0], klo);
+                    atomicMax(&ub[1], khi);
+                }
+            }
             const bool any_nan = __syncthreads_or(has_nan);
-            unsigned ka, kb;
-            row_select2_512(srow, n, (unsigned)((n - 1) / 2), hist, us, ka, kb);
-            float thr = (float)(0.5 * ((double)key2f(ka) + (double)key2f((n & 1) ? ka : kb)) - 10.0);
+            float v1, v2;
+            if (!row_median2_512(srow, n, key2f(ub[0]), key2f(ub[1]), hist, us, cand, v1, v2)) {
+                unsigned ka, kb;
+                row_select2_512(srow, n, (unsigned)((n - 1) / 2), hist, us, ka, kb);
+                v1 = key2f(ka);
+                v2 = key2f((n & 1) ? ka : kb);
+            }
+            float thr = (float)(0.5 * ((double)v1 + (double)v2) - 10.0);
             if (any_nan) thr = __int_as_float(0x7fc00000);
             float mx = -INFINITY, mn = INFINITY;
             double sm = 0.0;
