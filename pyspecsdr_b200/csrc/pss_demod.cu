@@ -762,7 +762,7 @@ __global__ void __launch_bounds__(FRAME_THREADS, 1)
 demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restrict__ audio, const long long n_frames,
                  const int plain /* 1: input is a real float32 row, no envelope / mean / normalisation */) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int N = D.N, C = D.C;
+    const int N = D.N, C = D.C, LC = 31 - __clz(C);       // C is a power of two
     const int n_chunks = (N + C - 1) / C;                 // <= FRAME_THREADS
     double* US = reinterpret_cast<double*>(smem);         // [(n_chunks + 2)][16] scan slots
     double* XS = US + (size_t)(FRAME_THREADS + 2) * 16;   // [32][16]
@@ -776,18 +776,46 @@ demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
         const float2* x = iq + frame * N;
         const float* xr = reinterpret_cast<const float*>(iq) + frame * N;
         __syncthreads();
-        // envelope (float32 hypot like np.abs on complex64) and its mean
+        // envelope (float32 hypot like np.abs on complex64) and its mean; 8 loads in flight per thread
         double sum = 0.0;
-        for (int i = tid; i < N; i += FRAME_THREADS) {
-            float e;
+        for (int ib = tid; ib < N; ib += FRAME_THREADS * 8) {
+            float e[8];
             if (plain) {
-                e = __ldg(xr + i);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = ib + u * FRAME_THREADS;
+                    e[u] = i < N ? __ldg(xr + i) : 0.f;
+                }
             } else {
-                const float2 v = __ldg(x + i);
-                e = hypotf(v.x, v.y);
+                float2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int i = ib + u * FRAME_THREADS;
+                    v[u] = i < N ? __ldcs(x + i) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float q = fmaf(v[u].x, v[u].x, v[u].y * v[u].y);
+                    // sqrt of the float sum is within 1 ulp of hypotf in the normal range; the scaled
+                    // library routine only where the squares over/underflow
+                    e[u] = (q > 1e-30f && q < 1e30f) ? __fsqrt_rn(q) : hypotf(v[u].x, v[u].y);
+                }
             }
-            row[i + i / C] = e;
-            sum += (double)e;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = ib + u * FRAME_THREADS;
+                if (i < N) {
+                    row[i + (i >> LC)] = e[u];
+                    sum += (double)e[u];
+                }
+            }
+        }
+        {   // next block of this CTA -> L2 while the recurrences run
+            const long long nf = frame + gridDim.x;
+            if (nf < n_frames && !plain) {
+                const char* nx = reinterpret_cast<const char*>(iq + nf * N);
+                for (int l = tid; l < N * 8 / 128; l += FRAME_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)l * 128));
+            }
         }
         for (int i = tid; i < (FRAME_THREADS + 2) * 16; i += FRAME_THREADS) US[i] = 0.0;
         sum = warp_sum(sum);
@@ -839,9 +867,10 @@ demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
         for (int w = 1; w < FRAME_THREADS / 32; ++w) m = fmax(m, redd[w]);
         float* dst = audio + frame * N;
         if (plain) {
-            for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = row[i + i / C];
+            for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = row[i + (i >> LC)];
         } else {
-            for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = (float)((double)row[i + i / C] / m * 0.95);
+            const double g = 0.95 / m;                    // y / max|y| * 0.95 (signal_processing.py:194)
+            for (int i = tid; i < N; i += FRAME_THREADS) __stcs(dst + i, (float)((double)row[i + (i >> LC)] * g));
         }
     }
 }
@@ -929,8 +958,8 @@ static int create_frame(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
     if (!d->sos || d->n_sections < 1 || d->n_sections > 5) return PSS_ERR_UNSUPPORTED;
     const int ns = d->n_sections;
     F.n_sections = ns;
-    F.C = (d->N + FRAME_THREADS - 1) / FRAME_THREADS;
-    if (F.C < 1) F.C = 1;
+    F.C = 1;                                               // samples per thread-chunk: power of two
+    while ((long long)F.C * FRAME_THREADS < d->N) F.C *= 2;
     const int n_chunks = (d->N + F.C - 1) / F.C;
     F.B = (n_chunks + 31) / 32;
     if (F.B < 1) F.B = 1;
