@@ -700,7 +700,23 @@ demod_fir_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
         const float2* x = iq + frame * N;
         __syncthreads();
         if (tid < 64) row[tid - 64] = 0.f;
-        for (int i = tid; i < n_rounds * ROUND; i += FRAME_THREADS) row[i] = i < N ? __ldg(x + i).x : 0.f;
+        for (int ib = tid; ib < n_rounds * ROUND; ib += FRAME_THREADS * 8) {      // ROUND = 8 * FRAME_THREADS
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int i = ib + u * FRAME_THREADS;
+                v[u] = i < N ? __ldcs(x + i).x : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) row[ib + u * FRAME_THREADS] = v[u];
+        }
+        {   // next block of this CTA -> L2 while the taps run
+            const long long nf = frame + gridDim.x;
+            if (nf < n_frames) {
+                const char* nx = reinterpret_cast<const char*>(iq + nf * N);
+                for (int l = tid; l < N * 8 / 128; l += FRAME_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)l * 128));
+            }
+        }
         __syncthreads();
         float mx = 0.f;
         // rounds walk the block from its end so the in-place overwrite never touches unread input
@@ -736,7 +752,8 @@ demod_fir_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
         mx = redf[0];
         for (int w = 1; w < FRAME_THREADS / 32; ++w) mx = fmaxf(mx, redf[w]);
         float* dst = audio + frame * N;
-        for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = (float)((double)row[i] / (double)mx * 0.95);
+        const double g = 0.95 / (double)mx;               // y / max|y| * 0.95 (signal_processing.py:216)
+        for (int i = tid; i < N; i += FRAME_THREADS) __stcs(dst + i, (float)((double)row[i] * g));
     }
 }
 
