@@ -101,6 +101,44 @@ def test_psd_epilogue_constant_row(ctx):
     np.testing.assert_allclose(res["stats"], -100.0, atol=TOL_DB)
 
 
+@pytest.mark.parametrize("n", [512, 4096, 8192, 16384, 32768, 65536])
+def test_psd_epilogue_flat_and_nearly_flat_rows(ctx, n):
+    """Rows whose median bucket holds (almost) every bin take the rare key-radix path of the median
+    select: all-zero input (every bin exactly -100 dB), a single impulse (|X|^2 constant up to
+    rounding, a handful of distinct floats), mixed with ordinary frames sharing the CTA / the grid."""
+    x = np.stack([np.zeros(n, np.complex64), synth.impulse(n, n // 3), synth.make("noise", n, seed=1),
+                  synth.impulse(n, 0), synth.make("tone40", n, seed=2), np.zeros(n, np.complex64)])
+    W = 97
+    res = ctx.psd(x, epilogue=True, W=W, want_stats=True)
+    for f in range(len(x)):
+        want = O.psd_epilogue(O.psd_db(x[f]))
+        assert np.max(np.abs(res["db"][f] - want)) <= TOL_DB, (n, f)
+        assert np.max(np.abs(res["cols"][f] - O.resample_cols(want, W))) <= TOL_DB
+        pk, av = O.peak_avg(want)
+        assert abs(res["stats"][f][0] - pk) <= TOL_DB and abs(res["stats"][f][1] - av) <= TOL_DB
+
+
+def test_psd_large_epilogue_many_frames_reuse_scratch(ctx):
+    # more frames than CTAs: every CTA of the persistent kernel reuses its L2 scratch and shared row
+    x = np.stack([synth.make(k, 16384, seed=9 + i) for i, k in enumerate(("tone40", "noise", "halfband"))])
+    many = np.tile(x, (110, 1))
+    res = ctx.psd(many, epilogue=True, W=200, want_stats=True)
+    for f in range(3):
+        want = O.psd_epilogue(O.psd_db(x[f]))
+        assert np.max(np.abs(res["db"][f] - want)) <= TOL_DB
+        assert np.all(res["db"][f::3] == res["db"][f])
+        assert np.all(res["cols"][f::3] == res["cols"][f])
+        assert np.all(res["stats"][f::3] == res["stats"][f])
+
+
+def test_psd_large_epilogue_65536(ctx):
+    x = synth.make("wbfm", 65536, seed=3)
+    res = ctx.psd(x, epilogue=True, W=200, want_stats=True)
+    want = O.psd_epilogue(O.psd_db(x))
+    assert np.max(np.abs(res["db"][0] - want)) <= TOL_DB
+    assert np.max(np.abs(res["cols"][0] - O.resample_cols(want, 200))) <= TOL_DB
+
+
 def test_psd_linearity_property(ctx):
     # size-independent property at a bench-sized frame: scaling the input by 2 adds 20*log10(2) dB
     x = frames("tone40", 4096, 2)
