@@ -251,6 +251,23 @@ int pss_sosfilt_f32(pss_ctx* ctx, const float* x, int N, int64_t n_frames, const
 int pss_power_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, float* power_db);
 int pss_audio_to_int16(pss_ctx* ctx, const float* audio, int64_t n, int16_t* pcm);
 
+/* ------------------------------------------------------------------ signal classifier
+ * classify_signal(samples, sample_rate, bandwidth), signal_processing.py:296-322: Welch PSD (scipy.signal.welch
+ * defaults at nperseg = 1024: periodic Hann, 50 % overlap, per-segment mean removal, density scaling, FFT-order
+ * two-sided output) -> estimate_bandwidth :267-280, estimate_modulation_index :283-293, spectral flatness :304
+ * -> decision tree :306-322.  The reference raises NameError at :299 (welch is never imported); this is the
+ * computation that line intends (opt-in in the Python shim, the default keeps raising like the reference).
+ * features [n_blocks][4] = signal_bw (Hz, FFT-order difference, may be negative like the reference's),
+ * modulation_index, spectral_flatness, peak dB of the Welch PSD;  label [n_blocks] = PSS_CLASS_*.
+ * N >= 1024 (scipy shrinks nperseg for shorter blocks; not mirrored: PSS_ERR_UNSUPPORTED).
+ */
+enum { PSS_CLASS_UNKNOWN = 0, PSS_CLASS_FM_BROADCAST = 1, PSS_CLASS_NARROW_FM = 2, PSS_CLASS_AM_BROADCAST = 3,
+       PSS_CLASS_SSB = 4, PSS_CLASS_DIGITAL = 5 };
+int pss_classify_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_blocks, double fs, double* features,
+                     int32_t* label);
+int pss_classify_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_blocks, double fs, double* features,
+                         int32_t* label);
+
 #ifdef __cplusplus
 }
 #endif

@@ -288,3 +288,43 @@ def scan_step(samples: np.ndarray, fs: float, threshold=None):
     mask = db > (peak - 20) if threshold is None else db > threshold
     count = int(np.sum(mask))
     return float(peak), count, count * (fs / len(db))
+
+
+# --------------------------------------------------------------------------- classifier (§8f-4)
+def classify_features(samples: np.ndarray, sample_rate: float):
+    """classify_signal's three features, signal_processing.py:267-304, with the one name the
+    reference forgets to import (`welch`, :299) supplied from scipy.signal.  Returns
+    (signal_bw, modulation_index, spectral_flatness) in the reference's dtypes."""
+    freqs, psd = _sig.welch(samples, fs=sample_rate, nperseg=1024)                       # :299
+    psd_db = 10 * np.log10(psd + 1e-10)                                                  # :270
+    mask = psd_db > (np.max(psd_db) + (-20))                                             # :271-274
+    fr = freqs[mask]
+    signal_bw = fr[-1] - fr[0] if np.any(mask) else 0                                    # :275-280
+    amp_var = np.var(np.abs(samples))                                                    # :286,290
+    phase_var = np.var(np.diff(np.unwrap(np.angle(samples))))                            # :287,291
+    modulation_index = phase_var / (amp_var + 1e-10)                                     # :293
+    spectral_flatness = np.exp(np.mean(np.log(psd + 1e-10))) / np.mean(psd)              # :304
+    return signal_bw, modulation_index, spectral_flatness
+
+
+def classify_label(signal_bw, modulation_index, spectral_flatness) -> str:
+    """The decision tree of classify_signal, signal_processing.py:306-322."""
+    if signal_bw > 150e3:
+        if modulation_index > 0.8:
+            return 'FM_BROADCAST'
+    elif 8e3 <= signal_bw <= 16e3:
+        if modulation_index < 0.3:
+            return 'NARROW_FM'
+    elif 8e3 <= signal_bw <= 10e3:
+        if modulation_index < 0.2 and spectral_flatness < 0.3:
+            return 'AM_BROADCAST'
+    elif 2e3 <= signal_bw <= 3e3:
+        if spectral_flatness < 0.2:
+            return 'SSB'
+    elif spectral_flatness > 0.7:
+        return 'DIGITAL'
+    return 'UNKNOWN'
+
+
+def classify_signal(samples: np.ndarray, sample_rate: float, bandwidth=None) -> str:
+    return classify_label(*classify_features(samples, sample_rate))

@@ -69,6 +69,8 @@ def _signatures():
         "pss_sosfilt_f32": (i32, [vp, vp, i32, i64, vp, i32, vp]),
         "pss_power_c64": (i32, [vp, vp, i32, i64, vp]),
         "pss_audio_to_int16": (i32, [vp, vp, i64, vp]),
+        "pss_classify_c64": (i32, [vp, vp, i32, i64, C.c_double, vp, vp]),
+        "pss_classify_c64_dev": (i32, [vp, vp, i32, i64, C.c_double, vp, vp]),
         "pss_display_quantise": (i32, [vp, vp, i64, i32, i32, vp, vp]),
         "pss_spectrum_normalise": (i32, [vp, vp, i32, i64, i32, vp, vp]),
         "pss_demod_plan_create": (i32, [vp, C.POINTER(DemodDesc), C.POINTER(vp)]),

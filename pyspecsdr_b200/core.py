@@ -303,6 +303,23 @@ class Context:
         self._ck(lib.pss_power_c64(self._h, x.ctypes.data, x.shape[1], x.shape[0], out.ctypes.data), "pss_power_c64")
         return out
 
+    CLASS_LABELS = ("UNKNOWN", "FM_BROADCAST", "NARROW_FM", "AM_BROADCAST", "SSB", "DIGITAL")
+
+    def classify(self, samples, fs: float):
+        """classify_signal's computation (signal_processing.py:296-322 with the missing `welch` import
+        supplied) per block -> (labels [list of str], features float64 [n_blocks, 4] = signal_bw,
+        modulation_index, spectral_flatness, Welch peak dB)."""
+        x = _as_frames(samples)
+        feat = np.empty((len(x), 4), np.float64)
+        lab = np.empty(len(x), np.int32)
+        self._ck(lib.pss_classify_c64(self._h, x.ctypes.data, x.shape[1], x.shape[0], float(fs), feat.ctypes.data,
+                                      lab.ctypes.data), "pss_classify_c64")
+        return [self.CLASS_LABELS[i] for i in lab], feat
+
+    def classify_dev(self, iq, N, n_blocks, fs, features, label):
+        self._ck(lib.pss_classify_c64_dev(self._h, _ptr(iq), N, n_blocks, float(fs), _ptr(features), _ptr(label)),
+                 "pss_classify_c64_dev")
+
     def to_int16(self, audio) -> np.ndarray:
         """write_audio_samples' numeric line (audio_processing.py:36-38): np.int16(samples * 32767)."""
         a = np.ascontiguousarray(audio, dtype=np.float32)

@@ -181,4 +181,24 @@ int pss_scan_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_steps, int use_
     return PSS_OK;
 }
 
+int pss_classify_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_blocks, double fs, double* features,
+                     int32_t* label) {
+    if (!ctx || !iq || !features || !label || n_blocks < 0 || N <= 0) return PSS_ERR_ARG;
+    if (n_blocks == 0) return PSS_OK;
+    PSS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t in_b = (size_t)n_blocks * N * 8;
+    int rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_in, &ctx->d_in_bytes, in_b))) return rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_aux, &ctx->d_aux_bytes, (size_t)n_blocks * 32))) return rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_aux2, &ctx->d_aux2_bytes, (size_t)n_blocks * 4))) return rc;
+    PSS_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, iq, in_b, cudaMemcpyHostToDevice, ctx->stream));
+    rc = pss_classify_c64_dev(ctx, (const float*)ctx->d_in, N, n_blocks, fs, (double*)ctx->d_aux, (int32_t*)ctx->d_aux2);
+    if (rc) return rc;
+    PSS_CUDA(ctx, cudaMemcpyAsync(features, ctx->d_aux, (size_t)n_blocks * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    PSS_CUDA(ctx, cudaMemcpyAsync(label, ctx->d_aux2, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PSS_OK;
+}
+
 }  // extern "C"
+

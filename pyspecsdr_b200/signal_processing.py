@@ -111,11 +111,21 @@ def bandpass_filter(data, lowcut, highcut, sample_rate):
     return _ctx().bandpass(np.asarray(data), float(lowcut), float(highcut), float(sample_rate))
 
 
+ENABLE_CLASSIFIER = False      # opt-in (or PSS_CLASSIFIER=1): see classify_signal
+
+
 def classify_signal(samples, sample_rate, bandwidth):
-    """signal_processing.py:296-322 raises NameError in the reference (`welch` is never imported);
-    callers catch it (pyspecsdr.py:2571).  Kept failing the same way: there is nothing to be at
-    parity with."""
-    raise NameError("name 'welch' is not defined")
+    """signal_processing.py:296-322.  In the reference this raises NameError (`welch` is never
+    imported, :299) and the callers catch it (pyspecsdr.py:2571), so by default it keeps failing the
+    same way.  With `ENABLE_CLASSIFIER = True` (or PSS_CLASSIFIER=1 in the environment) the intended
+    computation — scipy-default Welch PSD, estimate_bandwidth, estimate_modulation_index, spectral
+    flatness, the decision tree — runs on the GPU (`pss_classify_c64`); checked against the reference
+    executed with that one name supplied (tests/golden/classifier.npz)."""
+    import os
+    if not (ENABLE_CLASSIFIER or os.environ.get("PSS_CLASSIFIER") == "1"):
+        raise NameError("name 'welch' is not defined")
+    labels, _ = _ctx().classify(_c64(samples), float(sample_rate))
+    return labels[0]
 
 
 def _check_rate(target_rate):

@@ -212,3 +212,16 @@ def test_spectrum_display(golden):
             else:
                 ch, col = " ", 10
             assert cell == (ord(ch), (col << 8) | curses.A_BOLD), (x, y, v)
+
+
+def test_classifier_oracle_matches_reference_golden(golden):
+    """§8f-4: the oracle's classify_features / classify_label against the reference's own functions run
+    with the missing `welch` import supplied (oracle/make_golden_classifier.py)."""
+    from oracle.make_golden_classifier import CASES, make_case
+    g = golden("classifier")
+    for i, (name, kw, n, fs) in enumerate(CASES):
+        x = make_case(kw, n, seed=20 + i)
+        bw, mi, fl = O.classify_features(x, fs)
+        want = g[name + "_feat"]
+        assert bw == want[0] and mi == want[1] and fl == want[2], name
+        assert O.classify_label(bw, mi, fl) == str(g[name + "_label"]), name
