@@ -33,6 +33,7 @@ struct DecimDev {
 
 struct FrameDevFwd {
     int N = 0, n_taps = 0, n_sections = 0, C = 0, B = 0;
+    int T = 0, n_tiles = 1;     // long blocks run as n_tiles tiles of T samples (T == N when the block fits one CTA)
     const float* taps = nullptr;
     const double* sos = nullptr;
     const double* AC = nullptr;
@@ -48,6 +49,8 @@ struct pss_demod_plan {
     std::vector<void*> dev_allocs;
     void* U_scratch = nullptr;
     size_t U_scratch_bytes = 0;
+    void* tile_scratch = nullptr;       // per-block max|y| of tiled FIR plans
+    size_t tile_scratch_bytes = 0;
     // FIR / SOS plans (pss_demod_frame section)
     float* d_taps_f32 = nullptr;
     int n_taps = 0;
@@ -686,40 +689,49 @@ typedef FrameDevFwd FrameDev;   // C = samples per thread-chunk (AM), B = scan b
 // ---- USB / LSB: y = lfilter(taps, 1, x).real (the hilbert() round trip is the identity on the real
 // part and both side-band branches are identical), / max|y| * 0.95.
 __global__ void __launch_bounds__(FRAME_THREADS, 1)
-demod_fir_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restrict__ audio, const long long n_frames) {
+demod_fir_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restrict__ audio, const long long n_frames,
+                 unsigned* __restrict__ blkmax /* tiled plans: per-block max|y| (float bits), zeroed by the host */) {
     extern __shared__ __align__(16) unsigned char smem[];
-    float* row = reinterpret_cast<float*>(smem) + 64;     // [-64 .. n_rounds*ROUND): zero history in front
+    float* row = reinterpret_cast<float*>(smem) + 64;     // [-64 .. n_rounds*ROUND): history in front
     __shared__ float taps_s[FIR_MAX_TAPS + 3];
     __shared__ float redf[FRAME_THREADS / 32];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int N = D.N;
+    const int N = D.N, T = D.T, n_tiles = D.n_tiles;
     if (tid < FIR_MAX_TAPS) taps_s[tid] = tid < D.n_taps ? D.taps[tid] : 0.f;
     constexpr int OUT_PER = 8, ROUND = FRAME_THREADS * OUT_PER;
-    const int n_rounds = (N + ROUND - 1) / ROUND;
-    for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
-        const float2* x = iq + frame * N;
+    const int n_rounds = (T + ROUND - 1) / ROUND;
+    // work item = (block, tile); a block longer than one CTA's shared memory is cut into tiles of T
+    // samples, each tile re-reading the 64 samples in front of it; the peak normalisation of a tiled
+    // block is finished by frame_scale_kernel
+    for (long long item = blockIdx.x; item < n_frames * n_tiles; item += gridDim.x) {
+        const long long frame = item / n_tiles;
+        const int base = (int)(item - frame * n_tiles) * T;
+        const int len = min(T, N - base);
+        const float2* x = iq + frame * N + base;
         __syncthreads();
-        if (tid < 64) row[tid - 64] = 0.f;
+        if (tid < 64) row[tid - 64] = base > 0 ? __ldg(x + tid - 64).x : 0.f;      // lfilter starts from zero state
         for (int ib = tid; ib < n_rounds * ROUND; ib += FRAME_THREADS * 8) {      // ROUND = 8 * FRAME_THREADS
             float v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const int i = ib + u * FRAME_THREADS;
-                v[u] = i < N ? __ldcs(x + i).x : 0.f;
+                v[u] = i < len ? __ldcs(x + i).x : 0.f;
             }
 #pragma unroll
             for (int u = 0; u < 8; ++u) row[ib + u * FRAME_THREADS] = v[u];
         }
-        {   // next block of this CTA -> L2 while the taps run
-            const long long nf = frame + gridDim.x;
-            if (nf < n_frames) {
-                const char* nx = reinterpret_cast<const char*>(iq + nf * N);
-                for (int l = tid; l < N * 8 / 128; l += FRAME_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)l * 128));
+        {   // next work item of this CTA -> L2 while the taps run
+            const long long nx_item = item + gridDim.x;
+            if (nx_item < n_frames * n_tiles) {
+                const long long nf = nx_item / n_tiles;
+                const char* nx = reinterpret_cast<const char*>(iq + nf * N + (nx_item - nf * n_tiles) * T);
+                const int nl = min(T, N - (int)(nx_item - nf * n_tiles) * T);
+                for (int l = tid; l < nl * 8 / 128; l += FRAME_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)l * 128));
             }
         }
         __syncthreads();
         float mx = 0.f;
-        // rounds walk the block from its end so the in-place overwrite never touches unread input
+        // rounds walk the tile from its end so the in-place overwrite never touches unread input
         for (int r = n_rounds - 1; r >= 0; --r) {
             const int n0 = r * ROUND + tid * OUT_PER;
             float win[FIR_MAX_TAPS - 1 + 8];              // x[n0-64 .. n0+7]
@@ -743,7 +755,7 @@ demod_fir_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
             *reinterpret_cast<float4*>(row + n0 + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
 #pragma unroll
             for (int o = 0; o < 8; ++o)
-                if (n0 + o < N) mx = fmaxf(mx, fabsf(acc[o]));
+                if (n0 + o < len) mx = fmaxf(mx, fabsf(acc[o]));
             __syncthreads();
         }
         mx = warp_max(mx);
@@ -751,9 +763,24 @@ demod_fir_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
         __syncthreads();
         mx = redf[0];
         for (int w = 1; w < FRAME_THREADS / 32; ++w) mx = fmaxf(mx, redf[w]);
-        float* dst = audio + frame * N;
-        const double g = 0.95 / (double)mx;               // y / max|y| * 0.95 (signal_processing.py:216)
-        for (int i = tid; i < N; i += FRAME_THREADS) __stcs(dst + i, (float)((double)row[i] * g));
+        float* dst = audio + frame * N + base;
+        if (n_tiles == 1) {
+            const double g = 0.95 / (double)mx;               // y / max|y| * 0.95 (signal_processing.py:216)
+            for (int i = tid; i < len; i += FRAME_THREADS) __stcs(dst + i, (float)((double)row[i] * g));
+        } else {
+            for (int i = tid; i < len; i += FRAME_THREADS) dst[i] = row[i];
+            if (tid == 0) atomicMax(blkmax + frame, __float_as_uint(mx));      // mx >= 0 (NaN never wins, like fmaxf)
+        }
+    }
+}
+
+// Second half of the peak normalisation of tiled FIR plans: y * (0.95 / max|y|) per block, in place.
+__global__ void __launch_bounds__(256)
+frame_scale_kernel(float* __restrict__ audio, const int N, const long long n_frames, const unsigned* __restrict__ blkmax) {
+    const long long total = n_frames * N;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+        const double g = 0.95 / (double)__uint_as_float(blkmax[i / N]);
+        audio[i] = (float)((double)audio[i] * g);
     }
 }
 
@@ -780,100 +807,142 @@ demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
                  const int plain /* 1: input is a real float32 row, no envelope / mean / normalisation */) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int N = D.N, C = D.C, LC = 31 - __clz(C);       // C is a power of two
-    const int n_chunks = (N + C - 1) / C;                 // <= FRAME_THREADS
+    const int T = D.T, n_tiles = D.n_tiles;               // blocks longer than one CTA's shared memory: tiles of T = C * FRAME_THREADS
     double* US = reinterpret_cast<double*>(smem);         // [(n_chunks + 2)][16] scan slots
     double* XS = US + (size_t)(FRAME_THREADS + 2) * 16;   // [32][16]
     double* XB = XS + 512;                                // [32 groups][2][16] scan broadcast lines
     double* redd = XB + 1024;                             // [32]
-    float* row = reinterpret_cast<float*>(redd + 32);     // [N + N/C] skewed: idx + idx / C
+    float* row = reinterpret_cast<float*>(redd + 32);     // [T + T/C] skewed: idx + idx / C
+    __shared__ double carry[16];                          // filter state at the start of the current tile
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // the coefficients are read straight from the kernel-parameter constant bank (no registers)
     const double (&c)[5][5] = D.coef;
+    auto envelope = [](const float2 v) {
+        const float q = fmaf(v.x, v.x, v.y * v.y);
+        // sqrt of the float sum is within 1 ulp of hypotf in the normal range; the scaled library
+        // routine only where the squares over/underflow
+        return (q > 1e-30f && q < 1e30f) ? __fsqrt_rn(q) : hypotf(v.x, v.y);
+    };
     for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
-        const float2* x = iq + frame * N;
-        const float* xr = reinterpret_cast<const float*>(iq) + frame * N;
+        const float2* xb = iq + frame * N;
+        const float* xrb = reinterpret_cast<const float*>(iq) + frame * N;
+        float* dst = audio + frame * N;
+        float mean = 0.f;
         __syncthreads();
-        // envelope (float32 hypot like np.abs on complex64) and its mean; 8 loads in flight per thread
-        double sum = 0.0;
-        for (int ib = tid; ib < N; ib += FRAME_THREADS * 8) {
-            float e[8];
-            if (plain) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int i = ib + u * FRAME_THREADS;
-                    e[u] = i < N ? __ldg(xr + i) : 0.f;
-                }
-            } else {
+        if (n_tiles > 1 && !plain) {
+            // tiled block: the mean of the whole envelope is needed before the first tile is filtered
+            double sum = 0.0;
+            for (int ib = tid; ib < N; ib += FRAME_THREADS * 8) {
                 float2 v[8];
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
                     const int i = ib + u * FRAME_THREADS;
-                    v[u] = i < N ? __ldcs(x + i) : make_float2(0.f, 0.f);
+                    v[u] = i < N ? __ldg(xb + i) : make_float2(0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    if (ib + u * FRAME_THREADS < N) sum += (double)envelope(v[u]);
+            }
+            sum = warp_sum(sum);
+            if (lane == 0) redd[warp] = sum;
+            __syncthreads();
+            double tot = 0.0;
+            for (int w = 0; w < FRAME_THREADS / 32; ++w) tot += redd[w];
+            mean = (float)(tot / (double)N);
+        }
+        if (tid < 16) carry[tid] = 0.0;                   // sosfilt starts from zero state
+        float mx = 0.f;
+        for (int tile = 0; tile < n_tiles; ++tile) {
+            const int base = tile * T, len = min(T, N - base);
+            const int n_chunks = (len + C - 1) / C;       // <= FRAME_THREADS
+            const float2* x = xb + base;
+            const float* xr = xrb + base;
+            __syncthreads();
+            // envelope (float32 hypot like np.abs on complex64) and its mean; 8 loads in flight per thread
+            double sum = 0.0;
+            for (int ib = tid; ib < len; ib += FRAME_THREADS * 8) {
+                float e[8];
+                if (plain) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = ib + u * FRAME_THREADS;
+                        e[u] = i < len ? __ldg(xr + i) : 0.f;
+                    }
+                } else {
+                    float2 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = ib + u * FRAME_THREADS;
+                        v[u] = i < len ? __ldcs(x + i) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) e[u] = envelope(v[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const float q = fmaf(v[u].x, v[u].x, v[u].y * v[u].y);
-                    // sqrt of the float sum is within 1 ulp of hypotf in the normal range; the scaled
-                    // library routine only where the squares over/underflow
-                    e[u] = (q > 1e-30f && q < 1e30f) ? __fsqrt_rn(q) : hypotf(v[u].x, v[u].y);
+                    const int i = ib + u * FRAME_THREADS;
+                    if (i < len) {
+                        row[i + (i >> LC)] = e[u];
+                        sum += (double)e[u];
+                    }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int i = ib + u * FRAME_THREADS;
-                if (i < N) {
-                    row[i + (i >> LC)] = e[u];
-                    sum += (double)e[u];
+            if (n_tiles == 1) {   // next block of this CTA -> L2 while the recurrences run
+                const long long nf = frame + gridDim.x;
+                if (nf < n_frames && !plain) {
+                    const char* nx = reinterpret_cast<const char*>(iq + nf * N);
+                    for (int l = tid; l < N * 8 / 128; l += FRAME_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)l * 128));
                 }
             }
-        }
-        {   // next block of this CTA -> L2 while the recurrences run
-            const long long nf = frame + gridDim.x;
-            if (nf < n_frames && !plain) {
-                const char* nx = reinterpret_cast<const char*>(iq + nf * N);
-                for (int l = tid; l < N * 8 / 128; l += FRAME_THREADS) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)l * 128));
+            for (int i = tid; i < (FRAME_THREADS + 2) * 16; i += FRAME_THREADS) US[i] = i < 16 ? carry[i] : 0.0;   // slot 0 = start state
+            if (n_tiles == 1) {
+                sum = warp_sum(sum);
+                if (lane == 0) redd[warp] = sum;
             }
-        }
-        for (int i = tid; i < (FRAME_THREADS + 2) * 16; i += FRAME_THREADS) US[i] = 0.0;
-        sum = warp_sum(sum);
-        if (lane == 0) redd[warp] = sum;
-        __syncthreads();
-        double tot = 0.0;
-        for (int w = 0; w < FRAME_THREADS / 32; ++w) tot += redd[w];
-        const float mean = plain ? 0.f : (float)(tot / (double)N);    // np.mean(envelope), float32
-        // pass A: zero-state response end state of every chunk
-        const int i0 = tid * C, i1 = min(N, i0 + C);
-        const float* rp = row + i0 + tid;                              // skew: i0 / C == tid
-        if (tid < n_chunks) {
-            double z[NS][2];
-#pragma unroll
-            for (int s = 0; s < NS; ++s) z[s][0] = z[s][1] = 0.0;
-            for (int i = 0; i < i1 - i0; ++i) sos_step<NS>(c, z, (double)__fsub_rn(rp[i], mean));
-            double* u = US + (size_t)(tid + 1) * 16;
-#pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                u[2 * s] = z[s][0];
-                u[2 * s + 1] = z[s][1];
+            __syncthreads();
+            if (n_tiles == 1 && !plain) {
+                double tot = 0.0;
+                for (int w = 0; w < FRAME_THREADS / 32; ++w) tot += redd[w];
+                mean = (float)(tot / (double)N);                   // np.mean(envelope), float32
             }
-        }
-        __syncthreads();
-        // true state after every chunk: x_{c+1} = AC x_c + u_c, x_0 = 0 (slot 0 stays zero)
-        blocked_scan<16>(US, 16, 0, n_chunks, true, D.AC, D.ACB, D.B, US, XS, XB, tid);
-        // pass B: re-run from the true initial state (slot tid = state after chunk tid-1), in place
-        float mx = 0.f;
-        if (tid < n_chunks) {
-            double z[NS][2];
-            const double* u = US + (size_t)tid * 16;
+            // pass A: zero-state response end state of every chunk
+            const int i0 = tid * C, i1 = min(len, i0 + C);
+            const float* rp = row + i0 + tid;                              // skew: i0 / C == tid
+            if (tid < n_chunks) {
+                double z[NS][2];
 #pragma unroll
-            for (int s = 0; s < NS; ++s) {
-                z[s][0] = u[2 * s];
-                z[s][1] = u[2 * s + 1];
+                for (int s = 0; s < NS; ++s) z[s][0] = z[s][1] = 0.0;
+                for (int i = 0; i < i1 - i0; ++i) sos_step<NS>(c, z, (double)__fsub_rn(rp[i], mean));
+                double* u = US + (size_t)(tid + 1) * 16;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    u[2 * s] = z[s][0];
+                    u[2 * s + 1] = z[s][1];
+                }
             }
-            float* wp = row + i0 + tid;
-            for (int i = 0; i < i1 - i0; ++i) {
-                const float y = (float)sos_step<NS>(c, z, (double)__fsub_rn(wp[i], mean));
-                wp[i] = y;
-                mx = fmaxf(mx, fabsf(y));
+            __syncthreads();
+            // true state after every chunk: x_{c+1} = AC x_c + u_c, x_0 = the tile's start state (slot 0)
+            blocked_scan<16>(US, 16, 0, n_chunks, true, D.AC, D.ACB, D.B, US, XS, XB, tid);
+            // pass B: re-run from the true initial state (slot tid = state after chunk tid-1), in place
+            if (tid < n_chunks) {
+                double z[NS][2];
+                const double* u = US + (size_t)tid * 16;
+#pragma unroll
+                for (int s = 0; s < NS; ++s) {
+                    z[s][0] = u[2 * s];
+                    z[s][1] = u[2 * s + 1];
+                }
+                float* wp = row + i0 + tid;
+                for (int i = 0; i < i1 - i0; ++i) {
+                    const float y = (float)sos_step<NS>(c, z, (double)__fsub_rn(wp[i], mean));
+                    wp[i] = y;
+                    mx = fmaxf(mx, fabsf(y));
+                }
+            }
+            if (n_tiles > 1) {
+                __syncthreads();
+                if (tid < 16) carry[tid] = US[(size_t)n_chunks * 16 + tid];      // state after the tile's last chunk
+                for (int i = tid; i < len; i += FRAME_THREADS) dst[base + i] = row[i + (i >> LC)];
             }
         }
         mx = warp_max(mx);
@@ -882,12 +951,16 @@ demod_sos_kernel(const FrameDev D, const float2* __restrict__ iq, float* __restr
         __syncthreads();
         double m = redd[0];
         for (int w = 1; w < FRAME_THREADS / 32; ++w) m = fmax(m, redd[w]);
-        float* dst = audio + frame * N;
-        if (plain) {
-            for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = row[i + (i >> LC)];
-        } else {
-            const double g = 0.95 / m;                    // y / max|y| * 0.95 (signal_processing.py:194)
-            for (int i = tid; i < N; i += FRAME_THREADS) __stcs(dst + i, (float)((double)row[i + (i >> LC)] * g));
+        if (n_tiles == 1) {
+            if (plain) {
+                for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = row[i + (i >> LC)];
+            } else {
+                const double g = 0.95 / m;                    // y / max|y| * 0.95 (signal_processing.py:194)
+                for (int i = tid; i < N; i += FRAME_THREADS) __stcs(dst + i, (float)((double)row[i + (i >> LC)] * g));
+            }
+        } else if (!plain) {
+            const double g = 0.95 / m;                        // the unscaled tiles were written by this CTA
+            for (int i = tid; i < N; i += FRAME_THREADS) dst[i] = (float)((double)dst[i] * g);
         }
     }
 }
@@ -967,17 +1040,29 @@ static int create_frame(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
         F.taps = (const float*)p;
         F.n_taps = d->n_taps;
         const size_t round = (size_t)FRAME_THREADS * 8;
-        F.smem_bytes = (64 + ((size_t)d->N + round - 1) / round * round) * 4;
-        if (F.smem_bytes > 220 * 1024) return PSS_ERR_UNSUPPORTED;      // block too long for one CTA
+        F.T = d->N;
+        F.n_tiles = 1;
+        F.smem_bytes = (64 + ((size_t)F.T + round - 1) / round * round) * 4;
+        if (F.smem_bytes > 220 * 1024) {      // block too long for one CTA: tiles of 32768 samples
+            F.T = 32768;
+            F.n_tiles = (d->N + F.T - 1) / F.T;
+            F.smem_bytes = (64 + ((size_t)F.T + round - 1) / round * round) * 4;
+        }
         return PSS_OK;
     }
     // SOS
     if (!d->sos || d->n_sections < 1 || d->n_sections > 5) return PSS_ERR_UNSUPPORTED;
     const int ns = d->n_sections;
     F.n_sections = ns;
+    F.T = d->N;
+    F.n_tiles = 1;
+    if (d->N > 32768) {                                    // tiles of 64 samples x FRAME_THREADS chunks
+        F.T = 32768;
+        F.n_tiles = (d->N + F.T - 1) / F.T;
+    }
     F.C = 1;                                               // samples per thread-chunk: power of two
-    while ((long long)F.C * FRAME_THREADS < d->N) F.C *= 2;
-    const int n_chunks = (d->N + F.C - 1) / F.C;
+    while ((long long)F.C * FRAME_THREADS < F.T) F.C *= 2;
+    const int n_chunks = (F.T + F.C - 1) / F.C;
     F.B = (n_chunks + 31) / 32;
     if (F.B < 1) F.B = 1;
     // zero-input transition of one chunk, by stepping the cascade on unit states (padded to 16x16)
@@ -1020,7 +1105,7 @@ static int create_frame(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
     }
     if ((rc = upload(ctx, pl, AC.data(), 256 * 8, &p))) return rc; F.AC = (const double*)p;
     if ((rc = upload(ctx, pl, ACB.data(), 256 * 8, &p))) return rc; F.ACB = (const double*)p;
-    F.smem_bytes = ((size_t)(FRAME_THREADS + 2) * 16 * 8 + 512 * 8 + 1024 * 8 + 32 * 8 + ((size_t)d->N + d->N / F.C + 8) * 4 + 15) & ~(size_t)15;
+    F.smem_bytes = ((size_t)(FRAME_THREADS + 2) * 16 * 8 + 512 * 8 + 1024 * 8 + 32 * 8 + ((size_t)F.T + F.T / F.C + 8) * 4 + 15) & ~(size_t)15;
     if (F.smem_bytes > 220 * 1024) return PSS_ERR_UNSUPPORTED;
     return PSS_OK;
 }
@@ -1035,7 +1120,20 @@ static int launch_frame(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64
                                                                   pl->channels == 2 ? 1 : 0);
     } else if (pl->kind == PSS_PLAN_FIR) {
         PSS_CUDA(ctx, cudaFuncSetAttribute(demod_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.smem_bytes));
-        demod_fir_kernel<<<(unsigned)grid, FRAME_THREADS, F.smem_bytes, ctx->stream>>>(F, (const float2*)iq, audio, n_frames);
+        unsigned* blkmax = nullptr;
+        if (F.n_tiles > 1) {
+            int rc = pss_reserve(ctx, &pl->tile_scratch, &pl->tile_scratch_bytes, (size_t)n_frames * 4);
+            if (rc) return rc;
+            blkmax = (unsigned*)pl->tile_scratch;
+            PSS_CUDA(ctx, cudaMemsetAsync(blkmax, 0, (size_t)n_frames * 4, ctx->stream));
+            grid = ctx->sm_count;
+            if (grid > n_frames * F.n_tiles) grid = n_frames * F.n_tiles;
+        }
+        demod_fir_kernel<<<(unsigned)grid, FRAME_THREADS, F.smem_bytes, ctx->stream>>>(F, (const float2*)iq, audio, n_frames, blkmax);
+        if (F.n_tiles > 1) {
+            PSS_LAUNCH_CHECK(ctx);
+            frame_scale_kernel<<<(unsigned)(4 * ctx->sm_count), 256, 0, ctx->stream>>>(audio, F.N, n_frames, blkmax);
+        }
     } else {
 #define SOS_LAUNCH(NSv)                                                                                         \
     do {                                                                                                        \
@@ -1090,6 +1188,7 @@ void pss_demod_plan_destroy(pss_ctx* ctx, pss_demod_plan* pl) {
     }
     for (void* p : pl->dev_allocs) cudaFree(p);
     cudaFree(pl->U_scratch);
+    cudaFree(pl->tile_scratch);
     cudaFree(pl->d_taps_f32);
     cudaFree(pl->d_sos);
     delete pl;
