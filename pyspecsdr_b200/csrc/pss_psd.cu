@@ -586,6 +586,57 @@ psd_colfft_kernel(const float2* __restrict__ iq, const T* __restrict__ window, c
     for (int k1 = 0; k1 < N1; ++k1) dst[(long long)k1 * N2] = o[k1];
 }
 
+// Column transforms of the largest reads (N = N1 * 4096 with N1 = 64, 128, 256: 2^18 ... 2^20 points, the
+// app's SAMPLES = 10 ... 12, pyspecsdr.py:2236,2420-2422).  One CTA = 16 adjacent columns: window, N1-point
+// radix-2 DIF over the stride-4096 samples in shared memory, twiddle W_N^(n2*k1) from a two-level table,
+// fp64 rows Y[frame][k1][n2] for psd_kernel<12, double, EPI_RAW, LOG2N1>.  Availability path, not tuned.
+template <int LOG2N1>
+__global__ void __launch_bounds__(256)
+psd_colfft_big_kernel(const float2* __restrict__ iq, const double* __restrict__ window, const double2* __restrict__ tw1,
+                      const double2* __restrict__ thi, const double2* __restrict__ tlo, const long long n_frames,
+                      cx<double>* __restrict__ Y) {
+    constexpr int N1 = 1 << LOG2N1, N2 = 4096, COLS = 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cx<double>* buf = reinterpret_cast<cx<double>*>(smem_raw);           // [N1][COLS]
+    __shared__ double2 w1[N1 / 2];                                        // W_N1^k
+    const int tid = threadIdx.x;
+    const long long frame = blockIdx.x / (N2 / COLS);
+    const int c0 = (int)(blockIdx.x % (N2 / COLS)) * COLS;
+    if (frame >= n_frames) return;
+    const long long N = (long long)N1 * N2;
+    for (int k = tid; k < N1 / 2; k += 256) w1[k] = tw1[k];
+    const float2* src = iq + frame * N + c0;
+    for (int idx = tid; idx < N1 * COLS; idx += 256) {
+        const int n1 = idx / COLS, col = idx % COLS;
+        const float2 v = __ldg(src + (long long)n1 * N2 + col);
+        const double w = window ? __ldg(window + (long long)n1 * N2 + c0 + col) : 1.0;
+        buf[idx] = {(double)v.x * w, (double)v.y * w};
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int half = N1 / 2; half >= 1; half >>= 1) {
+        const int tstep = (N1 / 2) / half;
+        for (int b = tid; b < (N1 / 2) * COLS; b += 256) {
+            const int j = b / COLS, col = b % COLS;
+            const int pos = j % half, i0 = (j / half) * 2 * half + pos, i1 = i0 + half;
+            const cx<double> a = buf[i0 * COLS + col], c = buf[i1 * COLS + col];
+            const double2 w = w1[pos * tstep];
+            buf[i0 * COLS + col] = cadd(a, c);
+            buf[i1 * COLS + col] = cmul(csub(a, c), cx<double>{w.x, w.y});
+        }
+        __syncthreads();
+    }
+    cx<double>* dst = Y + frame * N + c0;
+    for (int idx = tid; idx < N1 * COLS; idx += 256) {
+        const int pos = idx / COLS, col = idx % COLS;
+        const int k1 = (int)(__brev((unsigned)pos) >> (32 - LOG2N1));     // DIF leaves bit-reversed order
+        const unsigned e = (unsigned)(c0 + col) * (unsigned)k1;           // < N
+        const double2 a = __ldg(thi + (e >> 10)), b = __ldg(tlo + (e & 1023u));
+        const cx<double> w = cmul(cx<double>{a.x, a.y}, cx<double>{b.x, b.y});
+        dst[(long long)k1 * N2 + col] = cmul(buf[idx], w);
+    }
+}
+
 // Row epilogue for rows that do not fit one CTA's shared memory: the same 5-bin smoothing, exact
 // median clamp, statistics and W-column resample as EPI_SMOOTH, streaming the row from L2.
 __global__ void __launch_bounds__(512)
@@ -1145,6 +1196,7 @@ static int get_tables(pss_ctx* ctx, int log2n, pss_fft_tables** out, bool fp32 =
 
 // Large transforms: N = 2^log2n with 14 <= log2n <= 17.
 struct LargeTables {
+    void *tw1 = nullptr, *thi = nullptr, *tlo = nullptr;   // big path: W_N1^k, W_N^(1024 j), W_N^j
     void* twN = nullptr;           // cx<double>[N2]: W_N^n2
     void* window[3] = {nullptr, nullptr, nullptr};
 };
@@ -1176,7 +1228,8 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
                      const pss_psd_out* out) {
     const int log2n2 = log2n == 17 ? 13 : 12;
     const int log2n1 = log2n - log2n2;
-    if (log2n1 < 2 || log2n1 > 4) return PSS_ERR_UNSUPPORTED;
+    if (log2n1 < 2 || log2n1 > 8 || log2n1 == 5) return PSS_ERR_UNSUPPORTED;
+    const bool big = log2n1 >= 6;          // 2^18 ... 2^20 points: shared-memory column transforms
     const long long N = 1LL << log2n, N2 = 1LL << log2n2;
     int rc;
     pss_fft_tables* tab2;
@@ -1192,6 +1245,22 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
         }
         PSS_CUDA(ctx, cudaMalloc(&lt.twN, N2 * sizeof(cx<double>)));
         PSS_CUDA(ctx, cudaMemcpy(lt.twN, tw.data(), N2 * sizeof(cx<double>), cudaMemcpyHostToDevice));
+        if (big) {
+            const long long N1 = 1LL << log2n1;
+            std::vector<cx<double>> t(1024);
+            auto put = [&](void** dst, long long count, long double num, long double den) -> int {
+                for (long long k = 0; k < count; ++k) {
+                    const long double a = -2.0L * PI * num * (long double)k / den;
+                    t[k] = {(double)cosl(a), (double)sinl(a)};
+                }
+                PSS_CUDA(ctx, cudaMalloc(dst, count * sizeof(cx<double>)));
+                PSS_CUDA(ctx, cudaMemcpy(*dst, t.data(), count * sizeof(cx<double>), cudaMemcpyHostToDevice));
+                return PSS_OK;
+            };
+            if ((rc = put(&lt.tw1, N1 / 2, 1.0L, (long double)N1))) return rc;          // W_N1^k
+            if ((rc = put(&lt.thi, N / 1024, 1024.0L, (long double)N))) return rc;       // W_N^(1024 j)
+            if ((rc = put(&lt.tlo, 1024, 1.0L, (long double)N))) return rc;              // W_N^j
+        }
         for (int kind = PSS_WINDOW_HAMMING; kind <= PSS_WINDOW_HANN; ++kind) {
             const long double a = kind == PSS_WINDOW_HAMMING ? 0.54L : 0.5L, b = kind == PSS_WINDOW_HAMMING ? 0.46L : 0.5L;
             for (long long i = 0; i < N; ++i) w[i] = (double)(a - b * cosl(2.0L * PI * (long double)i / (long double)(N - 1)));
@@ -1199,7 +1268,7 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
             PSS_CUDA(ctx, cudaMemcpy(lt.window[kind], w.data(), N * sizeof(double), cudaMemcpyHostToDevice));
         }
     }
-    if (log2n <= 16) {
+    if (log2n <= 16 && !big) {
         // fused persistent kernel: per-CTA scratch only (grid * N * 16 bytes of fp64 rows + the raw dB row)
         const bool smooth = epilogue == PSS_EPI_SMOOTH_CLAMP;
         const unsigned grid = (unsigned)(n_frames < ctx->sm_count ? n_frames : ctx->sm_count);
@@ -1246,7 +1315,20 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
         const long long threads = nf * N2;
         const unsigned grid = (unsigned)((threads + 255) / 256);
         cx<double>* Y = (cx<double>*)ctx->p_buf[7];
-        if (log2n1 == 2) psd_colfft_kernel<2, double><<<grid, 256, 0, ctx->stream>>>(src, win, (const cx<double>*)lt.twN, (int)N2, nf, Y);
+        if (big) {
+            const unsigned gb = (unsigned)(nf * (N2 / 16));
+            const size_t sm = (size_t)(1 << log2n1) * 16 * sizeof(cx<double>);
+#define PSS_BIG(L)                                                                                                   \
+    do {                                                                                                             \
+        PSS_CUDA(ctx, cudaFuncSetAttribute(psd_colfft_big_kernel<L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm)); \
+        psd_colfft_big_kernel<L><<<gb, 256, sm, ctx->stream>>>(src, win, (const double2*)lt.tw1, (const double2*)lt.thi, \
+                                                               (const double2*)lt.tlo, nf, Y);                       \
+    } while (0)
+            if (log2n1 == 6) PSS_BIG(6);
+            else if (log2n1 == 7) PSS_BIG(7);
+            else PSS_BIG(8);
+#undef PSS_BIG
+        } else if (log2n1 == 2) psd_colfft_kernel<2, double><<<grid, 256, 0, ctx->stream>>>(src, win, (const cx<double>*)lt.twN, (int)N2, nf, Y);
         else if (log2n1 == 3) psd_colfft_kernel<3, double><<<grid, 256, 0, ctx->stream>>>(src, win, (const cx<double>*)lt.twN, (int)N2, nf, Y);
         else psd_colfft_kernel<4, double><<<grid, 256, 0, ctx->stream>>>(src, win, (const cx<double>*)lt.twN, (int)N2, nf, Y);
         PSS_LAUNCH_CHECK(ctx);
@@ -1255,7 +1337,10 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
         p.ystage = Y;
         p.n_frames = nf << log2n1;
         p.db = epilogue == PSS_EPI_SMOOTH_CLAMP ? raw : out->db + f0 * N;
-        if (log2n2 == 13) rc = launch_stage_b<13, 4>(ctx, p);
+        if (log2n1 == 6) rc = launch_stage_b<12, 6>(ctx, p);
+        else if (log2n1 == 7) rc = launch_stage_b<12, 7>(ctx, p);
+        else if (log2n1 == 8) rc = launch_stage_b<12, 8>(ctx, p);
+        else if (log2n2 == 13) rc = launch_stage_b<13, 4>(ctx, p);
         else if (log2n1 == 2) rc = launch_stage_b<12, 2>(ctx, p);
         else if (log2n1 == 3) rc = launch_stage_b<12, 3>(ctx, p);
         else rc = launch_stage_b<12, 4>(ctx, p);

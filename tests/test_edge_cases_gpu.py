@@ -48,7 +48,7 @@ def test_error_paths_raise_instead_of_falling_back(ctx):
     with pytest.raises(PssError):                          # not a power of two
         ctx.psd(synth.make("noise", 1000, seed=0))
     with pytest.raises(PssError):                          # beyond the four-step path
-        ctx.psd(np.zeros(1 << 18, np.complex64))
+        ctx.psd(np.zeros(1 << 21, np.complex64))
     with pytest.raises(ValueError):                        # sample rate too low for a decimator
         ctx.demod(synth.make("noise", 4096, seed=0), 30e3, "NFM")
     with pytest.raises(ValueError):

@@ -131,6 +131,17 @@ def test_psd_large_epilogue_many_frames_reuse_scratch(ctx):
         assert np.all(res["stats"][f::3] == res["stats"][f])
 
 
+def test_psd_epilogue_largest_read(ctx):
+    # SAMPLES = 12: (2**12)*256 = 1 048 576-sample reads (pyspecsdr.py:2236, 2420-2422), main-loop epilogue included
+    x = synth.make("tone40", 1 << 20, seed=8)
+    res = ctx.psd(x, epilogue=True, W=200, want_stats=True)
+    want = O.psd_epilogue(O.psd_db(x))
+    assert np.max(np.abs(res["db"][0] - want)) <= TOL_DB
+    assert np.max(np.abs(res["cols"][0] - O.resample_cols(want, 200))) <= TOL_DB
+    pk, av = O.peak_avg(want)
+    assert abs(res["stats"][0][0] - pk) <= TOL_DB and abs(res["stats"][0][1] - av) <= TOL_DB
+
+
 def test_psd_large_epilogue_65536(ctx):
     x = synth.make("wbfm", 65536, seed=3)
     res = ctx.psd(x, epilogue=True, W=200, want_stats=True)
@@ -172,7 +183,7 @@ def test_scanner_vs_oracle_and_golden(ctx, golden):
         assert int(np.sum(db > -40 + 2 * TOL_DB)) <= count[k] <= int(np.sum(db > -40 - 2 * TOL_DB))
 
 
-@pytest.mark.parametrize("n", [16384, 32768, 65536, 131072])
+@pytest.mark.parametrize("n", [16384, 32768, 65536, 131072, 262144, 524288, 1048576])
 def test_psd_large_vs_oracle(ctx, n):
     # four-step path (column DFTs -> fp64 rows in an L2-sized scratch -> row FFTs)
     x = np.stack([synth.make(k, n, seed=n % 11 + i) for i, k in enumerate(("tone60", "wbfm", "noise"))])
