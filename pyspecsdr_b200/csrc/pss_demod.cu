@@ -26,7 +26,8 @@ struct DecimDev {
     float scale, norm;
     const double *tabF, *AF, *AFB, *AB, *ABB, *MB, *CR, *CB, *head, *tailT, *tailM;
     double DB;
-    int tab_in_smem, U_in_smem;
+    int tab_in_smem, U_in_smem, yout_in_smem;
+    long long yout_off;                         // doubles from the start of the CTA's global U slice (yout_in_smem == 0)
     int off_tile, off_misc, off_tab, off_U;     // byte offsets into dynamic shared memory
     size_t smem_bytes, U_bytes;
 };
@@ -288,10 +289,10 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
     double* dh = misc + 1024;          // [28] head discriminator samples
     double* red = dh + 32;             // [32] reduction scratch
     double* tres = red + 32;           // [SB + m_tail] tail result (<= 64)
-    double* yout = tres + 64;          // [n_out]
     const double* tab = D.tab_in_smem ? reinterpret_cast<const double*>(smem + D.off_tab) : D.tabF;
     double* U = D.U_in_smem ? reinterpret_cast<double*>(smem + D.off_U)
                             : U_global + (size_t)blockIdx.x * (D.U_bytes / 8);
+    double* yout = D.yout_in_smem ? tres + 64 : U + D.yout_off;      // [n_out]; long low-rate blocks keep it in L2
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int q = D.q, lead = D.lead, L = D.L, n_body = D.n_body, Kp = D.Kp;
 
@@ -604,17 +605,24 @@ static int create_decim(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
     // shared-memory layout: tile(s) + misc always; table and state slots when they fit in 113 KB.
     // Preference: 32-chunk double-buffered tiles, then smaller / single-buffered ones.
     const size_t budget = 113 * 1024;
-    const size_t misc_b = ((size_t)(512 + 512 + 32 + 32 + 64 + D.n_out) * 8 + 15) & ~(size_t)15;
+    // the un-normalised outputs stay in shared memory unless the block has more than 4096 of them (low
+    // sample rate x long read); then they live behind the state slots in the CTA's global slice
+    D.yout_in_smem = D.n_out <= 4096;
+    const size_t misc_b = ((size_t)(512 + 512 + 32 + 32 + 64 + (D.yout_in_smem ? D.n_out : 0)) * 8 + 15) & ~(size_t)15;
     const size_t tab_b = frag.size() * 8;
     D.U_bytes = (((size_t)(D.n_body + 2) * D.rows * 8) + 15) & ~(size_t)15;
-    const int cand[4][2] = {{32, 2}, {16, 2}, {32, 1}, {16, 1}};
+    if (!D.yout_in_smem) {
+        D.yout_off = (long long)(D.U_bytes / 8);
+        D.U_bytes += ((size_t)D.n_out * 8 + 15) & ~(size_t)15;
+    }
+    const int cand[5][2] = {{32, 2}, {16, 2}, {32, 1}, {16, 1}, {8, 1}};      // {8, 1}: q > ~1600 (fs > 36 MS/s)
     int pick = -1;
-    for (int c = 0; c < 4 && pick < 0; ++c) {
+    for (int c = 0; c < 5 && pick < 0; ++c) {
         size_t tf = (size_t)(cand[c][0] - 1) * D.q + D.Kp;
         if (tf * cand[c][1] < (size_t)D.tail_len) tf = ((size_t)D.tail_len + cand[c][1] - 1) / cand[c][1];
         tf = (tf + 3) & ~(size_t)3;
         const size_t tot = tf * 4 * cand[c][1] + misc_b + tab_b + D.U_bytes;
-        if (tot <= budget || c == 3) {
+        if (tot <= budget || c == 4) {
             pick = c;
             D.T = cand[c][0];
             D.nbuf = cand[c][1];
@@ -627,7 +635,7 @@ static int create_decim(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
     if (used > budget) return PSS_ERR_UNSUPPORTED;
     D.tab_in_smem = used + tab_b <= budget;
     if (D.tab_in_smem) { D.off_tab = (int)used; used += tab_b; }
-    D.U_in_smem = used + D.U_bytes <= budget;
+    D.U_in_smem = D.yout_in_smem && used + D.U_bytes <= budget;
     if (D.U_in_smem) { D.off_U = (int)used; used += D.U_bytes; }
     D.smem_bytes = used;
     pl->out_len = D.n_out;
@@ -663,12 +671,14 @@ static int launch_decim(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64
         if (D.T == 32 && D.nbuf == 2) DECIM_LAUNCH(8, 32, 2);
         else if (D.T == 16 && D.nbuf == 2) DECIM_LAUNCH(8, 16, 2);
         else if (D.T == 32) DECIM_LAUNCH(8, 32, 1);
-        else DECIM_LAUNCH(8, 16, 1);
+        else if (D.T == 16) DECIM_LAUNCH(8, 16, 1);
+        else DECIM_LAUNCH(8, 8, 1);
     } else {
         if (D.T == 32 && D.nbuf == 2) DECIM_LAUNCH(16, 32, 2);
         else if (D.T == 16 && D.nbuf == 2) DECIM_LAUNCH(16, 16, 2);
         else if (D.T == 32) DECIM_LAUNCH(16, 32, 1);
-        else DECIM_LAUNCH(16, 16, 1);
+        else if (D.T == 16) DECIM_LAUNCH(16, 16, 1);
+        else DECIM_LAUNCH(16, 8, 1);
     }
 #undef DECIM_LAUNCH
     PSS_LAUNCH_CHECK(ctx);

@@ -149,3 +149,23 @@ def test_bandpass_filter_long_row(ctx):
     got = ctx.bandpass(data, 1000.0, 2400.0, 22050.0)
     want = O.bandpass(data, 1000.0, 2400.0, 22050.0)
     assert np.sqrt(np.mean((got - want) ** 2)) <= 1e-5 * max(1.0, np.max(np.abs(want)))
+
+
+@pytest.mark.parametrize("fs,n", [(48e3, 32768), (250e3, 262144), (56e6, 32768), (61.44e6, 8192)])
+@pytest.mark.parametrize("mode", ["NFM", "WFM"])
+def test_decimating_demod_rate_extremes(ctx, mode, fs, n):
+    """Low rates x long reads (more than 4096 audio samples per block: un-normalised outputs and state slots
+    live in the CTA's L2 slice) and very high rates (q > 1600: 8-chunk tiles), tools/probe_rates.py."""
+    import warnings
+    x = synth.wbfm(n, seed=6, fs=fs, dev=min(75e3, fs / 8))
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref = O.demod(x, fs, mode)
+    except Exception:
+        with pytest.raises(Exception):      # e.g. WFM at 48 kHz: the reference's own filter design fails
+            ctx.demod(x, fs, mode)
+        return
+    got = ctx.demod(x, fs, mode)[0]
+    assert got.shape == ref.shape
+    assert float(np.sqrt(np.mean((got - ref) ** 2))) <= 1e-5
