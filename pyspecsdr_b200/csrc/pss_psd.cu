@@ -639,11 +639,16 @@ psd_colfft_big_kernel(const float2* __restrict__ iq, const double* __restrict__ 
 
 // Row epilogue for rows that do not fit one CTA's shared memory: the same 5-bin smoothing, exact
 // median clamp, statistics and W-column resample as EPI_SMOOTH, streaming the row from L2.
+__device__ __forceinline__ bool row_median2_512(const float* __restrict__ srow, const int n, const float lo,
+                                                const float hi, unsigned* hist, unsigned* us, float* cand,
+                                                float& v1, float& v2);
+
 __global__ void __launch_bounds__(512)
 row_epilogue_kernel(const float* __restrict__ raw, const int N, const long long n_frames, float* __restrict__ db,
                     float* __restrict__ cols, const int W, float* __restrict__ stats) {
-    __shared__ unsigned hist[256];
-    __shared__ unsigned us[8];
+    __shared__ unsigned hist[512];
+    __shared__ unsigned us[8], ub[2];
+    __shared__ float cand[64];
     __shared__ double dsum[16];
     __shared__ float fmx[16], fmn[16];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -651,94 +656,37 @@ row_epilogue_kernel(const float* __restrict__ raw, const int N, const long long 
     for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
         const float* d = raw + f * N;
         float* s = db + f * n;
-        if (tid < 8) us[tid] = (tid == 0 || tid == 5) ? 0xffffffffu : 0u;
+        if (tid < 8) us[tid] = tid == 3 ? 0xffffffffu : 0u;
+        if (tid < 2) ub[tid] = tid == 0 ? 0xffffffffu : 0u;
         __syncthreads();
-        unsigned kmin = 0xffffffffu, kmax = 0u;
+        // 5-bin means; the raw row's min / max bound them (linear buckets of the 2-level median)
+        float rlo = INFINITY, rhi = -INFINITY;
         bool has_nan = false;
         for (int i = tid; i < n; i += 512) {
             const float v = ((d[i] + d[i + 1]) + (d[i + 2] + d[i + 3]) + d[i + 4]) * 0.2f;
             s[i] = v;
-            const unsigned k = f2key(v);
-            kmin = min(kmin, k);
-            kmax = max(kmax, k);
+            rlo = fminf(rlo, fminf(d[i], d[i + 4]));
+            rhi = fmaxf(rhi, fmaxf(d[i], d[i + 4]));
             has_nan |= (v != v);
         }
-        kmin = __reduce_min_sync(0xffffffffu, kmin);
-        kmax = __reduce_max_sync(0xffffffffu, kmax);
-        if (lane == 0) {
-            atomicMin(&us[0], kmin);
-            atomicMax(&us[1], kmax);
-        }
-        if (__any_sync(0xffffffffu, has_nan) && lane == 0) atomicOr(&us[6], 1u);
-        __syncthreads();
-        kmin = us[0];
-        kmax = us[1];
-        const int common = min(__clz((int)(kmin ^ kmax)), 31);
-        unsigned rank = (unsigned)((n - 1) / 2), prefix = 0u;
-        for (int ps = 0; ps < 4; ++ps) {
-            const int shift = 24 - 8 * ps;
-            if (tid < 256) hist[tid] = 0u;
-            __syncthreads();
-            for (int i = tid; i < n; i += 512) {
-                const unsigned k = (f2key(s[i]) - kmin) << common;
-                if (ps == 0 || (k >> (shift + 8)) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (warp == 0) {
-                unsigned c[8], sum = 0;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    c[q] = hist[8 * lane + q];
-                    sum += c[q];
-                }
-                unsigned incl = sum;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += up;
-                }
-                const unsigned hit = __ballot_sync(0xffffffffu, incl > rank);
-                const int Ln = __ffs(hit) - 1;
-                if (lane == Ln) {
-                    unsigned r = rank - (incl - sum);
-                    int dg = 0;
-                    bool found = false;
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        if (!found) {
-                            if (r < c[q]) { dg = q; found = true; }
-                            else r -= c[q];
-                        }
-                    }
-                    us[2] = (unsigned)(8 * lane + dg);
-                    us[3] = r;
-                }
-            }
-            __syncthreads();
-            prefix = (prefix << 8) | us[2];
-            rank = us[3];
-        }
-        const unsigned key1n = prefix;
-        unsigned cnt_le = 0, min_gt = 0xffffffffu;
-        for (int i = tid; i < n; i += 512) {
-            const unsigned k = (f2key(s[i]) - kmin) << common;
-            cnt_le += k <= key1n;
-            if (k > key1n) min_gt = min(min_gt, k);
-        }
-        cnt_le = __reduce_add_sync(0xffffffffu, cnt_le);
-        min_gt = __reduce_min_sync(0xffffffffu, min_gt);
-        if (lane == 0) {
-            atomicAdd(&us[4], cnt_le);
-            atomicMin(&us[5], min_gt);
-        }
-        __syncthreads();
-        float thr;
         {
-            const unsigned key2n = ((n & 1) || us[4] > (unsigned)(n / 2)) ? key1n : us[5];
-            const float v1 = key2f((key1n >> common) + kmin), v2 = key2f((key2n >> common) + kmin);
-            thr = (float)(0.5 * ((double)v1 + (double)v2) - 10.0);
-            if (us[6]) thr = __int_as_float(0x7fc00000);
+            const unsigned klo = __reduce_min_sync(0xffffffffu, f2key(rlo));
+            const unsigned khi = __reduce_max_sync(0xffffffffu, f2key(rhi));
+            if (lane == 0) {
+                atomicMin(&ub[0], klo);
+                atomicMax(&ub[1], khi);
+            }
         }
+        const bool any_nan = __syncthreads_or(has_nan);
+        float v1, v2;
+        if (!row_median2_512(s, n, key2f(ub[0]), key2f(ub[1]), hist, us, cand, v1, v2)) {
+            unsigned ka, kb;
+            row_select2_512(s, n, (unsigned)((n - 1) / 2), hist, us, ka, kb);
+            v1 = key2f(ka);
+            v2 = key2f((n & 1) ? ka : kb);
+        }
+        float thr = (float)(0.5 * ((double)v1 + (double)v2) - 10.0);
+        if (any_nan) thr = __int_as_float(0x7fc00000);
         float mx = -INFINITY, mn = INFINITY;
         double sm = 0.0;
         for (int i = tid; i < n; i += 512) {
@@ -768,8 +716,8 @@ row_epilogue_kernel(const float* __restrict__ raw, const int N, const long long 
             }
             const float nanv = __int_as_float(0x7fc00000);
             float4 st;
-            st.x = us[6] ? nanv : a;
-            st.y = us[6] ? nanv : (float)(t / n);
+            st.x = any_nan ? nanv : a;
+            st.y = any_nan ? nanv : (float)(t / n);
             st.z = b;
             st.w = a;
             reinterpret_cast<float4*>(stats)[f] = st;
@@ -1302,14 +1250,26 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
     if (sub < 1) sub = 1;
     if (sub > n_frames) sub = n_frames;
     if ((rc = pss_reserve(ctx, &ctx->p_buf[7], &ctx->p_bytes[7], (size_t)sub * N * 16))) return rc;
+    // with an epilogue the raw rows of up to 2*SMs frames (<= 512 MB) are collected first, so the row
+    // epilogue runs one CTA per frame over a full grid instead of once per small sub-batch
+    const bool smooth = epilogue == PSS_EPI_SMOOTH_CLAMP;
+    long long eb = n_frames;
     float* raw = out->db;
-    if (epilogue == PSS_EPI_SMOOTH_CLAMP) {
-        if ((rc = pss_reserve(ctx, &ctx->p_buf[9], &ctx->p_bytes[9], (size_t)sub * N * 4))) return rc;
+    if (smooth) {
+        eb = 2LL * ctx->sm_count;
+        const long long cap = (512LL << 20) / (N * 4);
+        if (eb > cap) eb = cap;
+        if (eb < sub) eb = sub;
+        if (eb > n_frames) eb = n_frames;
+        eb = (eb / sub) * sub > 0 ? (eb / sub) * sub : sub;           // whole sub-batches
+        if ((rc = pss_reserve(ctx, &ctx->p_buf[9], &ctx->p_bytes[9], (size_t)eb * N * 4))) return rc;
         raw = (float*)ctx->p_buf[9];
     }
-    const long long n_out = epilogue == PSS_EPI_SMOOTH_CLAMP ? N - 4 : N;
-    for (int64_t f0 = 0; f0 < n_frames; f0 += sub) {
-        const long long nf = n_frames - f0 < sub ? n_frames - f0 : sub;
+    const long long n_out = smooth ? N - 4 : N;
+    for (int64_t e0 = 0; e0 < n_frames; e0 += eb) {
+    const long long ne = n_frames - e0 < eb ? n_frames - e0 : eb;
+    for (int64_t f0 = e0; f0 < e0 + ne; f0 += sub) {
+        const long long nf = e0 + ne - f0 < sub ? e0 + ne - f0 : sub;
         const float2* src = reinterpret_cast<const float2*>(iq) + f0 * N;
         const double* win = window == PSS_WINDOW_NONE ? nullptr : (const double*)lt.window[window];
         const long long threads = nf * N2;
@@ -1336,7 +1296,7 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
         p.tw = tab2->twiddle;
         p.ystage = Y;
         p.n_frames = nf << log2n1;
-        p.db = epilogue == PSS_EPI_SMOOTH_CLAMP ? raw : out->db + f0 * N;
+        p.db = smooth ? raw + (f0 - e0) * N : out->db + f0 * N;
         if (log2n1 == 6) rc = launch_stage_b<12, 6>(ctx, p);
         else if (log2n1 == 7) rc = launch_stage_b<12, 7>(ctx, p);
         else if (log2n1 == 8) rc = launch_stage_b<12, 8>(ctx, p);
@@ -1345,20 +1305,21 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
         else if (log2n1 == 3) rc = launch_stage_b<12, 3>(ctx, p);
         else rc = launch_stage_b<12, 4>(ctx, p);
         if (rc) return rc;
-        if (epilogue == PSS_EPI_SMOOTH_CLAMP) {
-            // the smoothed row is always produced (median/clamp work on it); use scratch when the caller
-            // does not want it
-            float* dbo = out->db ? out->db + f0 * n_out : nullptr;
-            if (!dbo) {
-                if ((rc = pss_reserve(ctx, &ctx->p_buf[8], &ctx->p_bytes[8], (size_t)sub * n_out * 4))) return rc;
-                dbo = (float*)ctx->p_buf[8];
-            }
-            const unsigned g2 = (unsigned)(nf < 2LL * ctx->sm_count ? nf : 2LL * ctx->sm_count);
-            row_epilogue_kernel<<<g2, 512, 0, ctx->stream>>>(raw, (int)N, nf, dbo,
-                                                            out->cols ? out->cols + f0 * out->W : nullptr, out->W,
-                                                            out->stats ? out->stats + f0 * 4 : nullptr);
-            PSS_LAUNCH_CHECK(ctx);
+    }
+    if (smooth) {
+        // the smoothed row is always produced (median/clamp work on it); use scratch when the caller
+        // does not want it
+        float* dbo = out->db ? out->db + e0 * n_out : nullptr;
+        if (!dbo) {
+            if ((rc = pss_reserve(ctx, &ctx->p_buf[8], &ctx->p_bytes[8], (size_t)eb * n_out * 4))) return rc;
+            dbo = (float*)ctx->p_buf[8];
         }
+        const unsigned g2 = (unsigned)(ne < 2LL * ctx->sm_count ? ne : 2LL * ctx->sm_count);
+        row_epilogue_kernel<<<g2, 512, 0, ctx->stream>>>(raw, (int)N, ne, dbo,
+                                                        out->cols ? out->cols + e0 * out->W : nullptr, out->W,
+                                                        out->stats ? out->stats + e0 * 4 : nullptr);
+        PSS_LAUNCH_CHECK(ctx);
+    }
     }
     return PSS_OK;
 }

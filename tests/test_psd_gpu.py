@@ -101,7 +101,7 @@ def test_psd_epilogue_constant_row(ctx):
     np.testing.assert_allclose(res["stats"], -100.0, atol=TOL_DB)
 
 
-@pytest.mark.parametrize("n", [512, 4096, 8192, 16384, 32768, 65536])
+@pytest.mark.parametrize("n", [512, 4096, 8192, 16384, 32768, 65536, 131072])
 def test_psd_epilogue_flat_and_nearly_flat_rows(ctx, n):
     """Rows whose median bucket holds (almost) every bin take the rare key-radix path of the median
     select: all-zero input (every bin exactly -100 dB), a single impulse (|X|^2 constant up to
@@ -140,6 +140,19 @@ def test_psd_epilogue_largest_read(ctx):
     assert np.max(np.abs(res["cols"][0] - O.resample_cols(want, 200))) <= TOL_DB
     pk, av = O.peak_avg(want)
     assert abs(res["stats"][0][0] - pk) <= TOL_DB and abs(res["stats"][0][1] - av) <= TOL_DB
+
+
+def test_psd_131072_epilogue_many_frames(ctx):
+    # more frames than one L2-sized sub-batch (32) and than one epilogue batch (2 * SMs): scratch reuse
+    x = np.stack([synth.make(k, 131072, seed=2 + i) for i, k in enumerate(("tone40", "noise", "wbfm"))])
+    many = np.tile(x, (101, 1))
+    res = ctx.psd(many, epilogue=True, W=200, want_stats=True)
+    for f in range(3):
+        want = O.psd_epilogue(O.psd_db(x[f]))
+        assert np.max(np.abs(res["db"][f] - want)) <= TOL_DB
+        assert np.all(res["db"][f::3] == res["db"][f])
+        assert np.all(res["cols"][f::3] == res["cols"][f])
+        assert np.all(res["stats"][f::3] == res["stats"][f])
 
 
 def test_psd_large_epilogue_65536(ctx):

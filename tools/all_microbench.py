@@ -58,5 +58,12 @@ for mode in os.environ.get("DEMOD_MODES", "NFM,WFM,AM,USB,RAW").split(","):
     b = F * N * 8 + audio.numel() * 4
     rows.append({"kernel": "demod", "mode": mode, "ms": ms, "GSps": F * N / ms / 1e6, "frac": b / ms / 1e6 / peak})
     print(rows[-1], flush=True)
+if os.environ.get("CLASSIFY", "1") == "1":
+    feat = torch.empty(F, 4, device="cuda", dtype=torch.float64)
+    lab = torch.empty(F, device="cuda", dtype=torch.int32)
+    x = iq.view(F, N, 2)
+    ms = timeit(lambda: ctx.classify_dev(x, N, F, 2.4e6, feat, lab), reps=5)
+    rows.append({"kernel": "classify", "ms": ms, "GSps": F * N / ms / 1e6, "frac": F * N * 8 / ms / 1e6 / peak})
+    print(rows[-1], flush=True)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/all_microbench.json", "w"), indent=1)

@@ -13,5 +13,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv \
 ncu --set full --clock-control none --import-source on -k regex:'psd_kernel|demod_decim_kernel|display_render' \
     -s 9 -c 3 -o gpurun_out/bench_kernels_${R} python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 1 \
     > gpurun_out/bench_full_ncu_${R}.log 2>&1
-tail -2 gpurun_out/pytest_gpu_${R}.log gpurun_out/smoke_${R}.log
+tail -n 2 gpurun_out/pytest_gpu_${R}.log gpurun_out/smoke_${R}.log
 tail -c 600 gpurun_out/bench_${R}.json
