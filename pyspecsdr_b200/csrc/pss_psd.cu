@@ -129,9 +129,9 @@ __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<
 // LOG2N1 > 0: this launch is the second stage of a length N*2^LOG2N1 transform (four-step FFT): frame
 // index = big_frame * N1 + k1, input = column-transformed, twiddled fp64 rows, output bin = k1 + N1*k2.
 template <int LOG2N, typename T, int EPI, int LOG2N1 = 0>
-// The smoothing/median epilogue is latency-bound (barriers, shared-memory atomics), so that variant
-// is held to 80 registers for 3 CTAs/SM (measured +14 %; ptxas fits the radix-16 passes without
-// spills); the raw variant is fp64-pipe-bound and is faster at 2 CTAs/SM with ~110 registers.
+// Occupancy of the 64 KB-per-CTA configurations: 2 CTAs/SM at ~110-120 registers for every variant
+// (PSS_SMOOTH_MINB).  With the 13-barrier key radix select the smoothing variant was faster at 3 CTAs/SM
+// held to 80 registers; with the 6-barrier two-level median 2 CTAs/SM wins by 6 %.
 __global__ void __launch_bounds__(PsdCfg<LOG2N, T>::THREADS,
                                   (EPI == EPI_SMOOTH && PsdCfg<LOG2N, T>::MINB == 2) ? PSS_SMOOTH_MINB : PsdCfg<LOG2N, T>::MINB)
 psd_kernel(const PsdParams p) {
