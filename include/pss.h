@@ -72,7 +72,8 @@ void        pss_host_free(void* p);
  *      + header peak/avg                        pyspecsdr.py:388-389
  *      + the W-column np.interp resample every draw_* does (pyspecsdr.py:448-452, 1378-1382, ...)
  * One fused kernel: window -> radix-16 Stockham FFT (fp64) -> fftshift -> 10*log10(|X|^2+1e-10).
- * N must be a power of two, 64 <= N <= 131072.  n_out = N (RAW) or N-4 (SMOOTH_CLAMP).
+ * N must be a power of two, 64 <= N <= 1048576 (every read size of the app, pyspecsdr.py:2236,2415-2422).
+ * n_out = N (RAW) or N-4 (SMOOTH_CLAMP).
  * precision = PSS_PREC_FP64 is the parity path.  PSS_PREC_FP32 is an explicit fast mode (RAW epilogue,
  * N <= 8192) that runs window, butterflies and power in float: it does NOT meet the 1e-4 dB bar when
  * a strong carrier is present (errors up to ~0.1-0.5 dB in bins 60 dB under a tone) and is never
