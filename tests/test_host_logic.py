@@ -165,3 +165,15 @@ def test_capture_block_ranges_and_format(tmp_path):
     np.save(path, x.astype(np.complex128))
     with pytest.raises(ValueError):
         capture.open_capture(path)
+
+
+def test_tools_and_bench_compile():
+    """The GPU-side scripts under tools/ (and bench.py, __graft_entry__.py) at least parse: they only run on the
+    B200 box, a syntax error there costs a gpurun call."""
+    import glob
+    import py_compile
+    files = sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))) + [os.path.join(ROOT, "bench.py"),
+                                                                        os.path.join(ROOT, "__graft_entry__.py")]
+    assert len(files) >= 8
+    for f in files:
+        py_compile.compile(f, doraise=True)
