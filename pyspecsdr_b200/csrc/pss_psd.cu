@@ -95,7 +95,7 @@ struct HalfBarrier {
     __device__ __forceinline__ void operator()() const { asm volatile("bar.sync %0, 256;" ::"r"(id) : "memory"); }
 };
 
-template <int LOG2N, int P, typename T, typename OutF, typename Bar = CtaBarrier>
+template <int LOG2N, int P, typename T, bool PAD = false, typename OutF, typename Bar = CtaBarrier>
 __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<T>* __restrict__ wpre,
                                               const int t, OutF&& out, Bar bar = Bar()) {
     constexpr int N = 1 << LOG2N, TPF = N / 16;
@@ -103,9 +103,14 @@ __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<
     constexpr int TI = N / R, ITEMS = 16 / R, NP = pss_num_passes(LOG2N);
     cx<T> v[16];
 #pragma unroll
-    for (int it = 0; it < ITEMS; ++it)
+    for (int it = 0; it < ITEMS; ++it) {
+        const cx<T>* rb = buf + fft_pad(t + it * TPF);           // PAD: per-thread base + compile-time offsets
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[it * R + r] = buf[fft_swz(t + it * TPF + r * TI)];
+        for (int r = 0; r < R; ++r) {
+            if constexpr (PAD && TI % 16 == 0) v[it * R + r] = rb[fft_padded(r * TI)];
+            else v[it * R + r] = buf[fft_swz(t + it * TPF + r * TI)];
+        }
+    }
     bar();
 #pragma unroll
     for (int it = 0; it < ITEMS; ++it) {
@@ -114,11 +119,14 @@ __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<
         twiddle_apply<R, T>(v + it * R, wpre[it]);
         fft_regs<R, T>::run(v + it * R);
         const int base = ((j - k) << BITS) + k;
+        cx<T>* wb = buf + fft_pad(base);
 #pragma unroll
         for (int p = 0; p < R; ++p) {
             const int idx = base + fft_perm<R>(p) * NS;
             if constexpr (P == NP - 1)
                 out(idx, v[it * R + p]);
+            else if constexpr (PAD)
+                wb[fft_padded(fft_perm<R>(p) * NS)] = v[it * R + p];      // NS = 16^P: a multiple of 16
             else
                 buf[fft_swz(idx)] = v[it * R + p];
         }
@@ -865,7 +873,7 @@ struct PsdLargeParams {
 template <int LOG2N, int EPI>
 __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams p) {
     constexpr int N = 1 << LOG2N, LOG2N1 = LOG2N - 12, N1 = 1 << LOG2N1, N2 = 4096, n = N - 4;
-    constexpr bool SROW_SMEM = (size_t)N * 4 <= 2 * N2 * sizeof(cx<double>);
+    constexpr bool SROW_SMEM = (size_t)N * 4 <= 2 * fft_padded(N2) * sizeof(cx<double>);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned hist[512];
     __shared__ unsigned us[8], ub[2];
@@ -873,7 +881,7 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
     __shared__ double dsum_s[16];
     __shared__ float fmx_s[16], fmn_s[16];
     const int tid = threadIdx.x, g = tid >> 8, t = tid & 255, lane = tid & 31, warp = tid >> 5;
-    cx<double>* buf = reinterpret_cast<cx<double>*>(smem_raw) + (size_t)g * N2;
+    cx<double>* buf = reinterpret_cast<cx<double>*>(smem_raw) + (size_t)g * fft_padded(N2);
     const HalfBarrier hbar{1 + g};
     cx<double> wpre[2];
     wpre[0] = p.tw[t & 15];                       // pass 1: ns = 16, offset 0
@@ -937,7 +945,7 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
                 fft_regs<16, double>::run(v);
                 const int base = t << 4;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) buf[fft_swz(base + fft_perm<16>(q))] = v[q];
+                for (int q = 0; q < 16; ++q) buf[fft_pad(base) + fft_perm<16>(q)] = v[q];      // base = 16 t
             }
             hbar();
             auto emit = [&](int k, const cx<double> X) {
@@ -946,8 +954,8 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
                 if constexpr (EPI == EPI_RAW) p.db[frame * N + pos] = d;
                 else st_keep(raw + pos, d, keep);
             };
-            stockham_pass<12, 1, double>(buf, &wpre[0], t, [](int, cx<double>) {}, hbar);
-            stockham_pass<12, 2, double>(buf, &wpre[1], t, emit, hbar);
+            stockham_pass<12, 1, double, true>(buf, &wpre[0], t, [](int, cx<double>) {}, hbar);
+            stockham_pass<12, 2, double, true>(buf, &wpre[1], t, emit, hbar);
         }
         __syncthreads();
         if constexpr (EPI == EPI_SMOOTH) {
@@ -1165,7 +1173,7 @@ static int launch_stage_b(pss_ctx* ctx, const PsdParams& p) {
 template <int LOG2N, int EPI>
 static int launch_large_fused(pss_ctx* ctx, const PsdLargeParams& p, unsigned grid) {
     auto kern = psd_large_kernel<LOG2N, EPI>;
-    constexpr int SMEM = 2 * 4096 * (int)sizeof(cx<double>);
+    constexpr int SMEM = 2 * fft_padded(4096) * (int)sizeof(cx<double>);
     PSS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     kern<<<grid, 512, SMEM, ctx->stream>>>(p);
     PSS_LAUNCH_CHECK(ctx);
