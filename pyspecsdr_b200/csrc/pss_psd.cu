@@ -1504,14 +1504,25 @@ classify_kernel(const float2* __restrict__ iq, const int N_block, const long lon
         const float2* x = iq + b * N_block;
         const float PI_F = 3.14159274101257324f, TWO_PI_F = 6.28318548202514648f;
         double sa = 0.0, saa = 0.0, sd = 0.0, sdd = 0.0;
-        for (int i = tid; i < N_block; i += 256) {
-            const float2 s0 = __ldg(x + i);
+#pragma unroll 4
+        for (int ib = 0; ib < N_block; ib += 256) {          // uniform trip count: the shuffle below needs whole warps
+            const int i = ib + tid;
+            const bool in = i < N_block;
+            const float2 s0 = in ? __ldg(x + i) : make_float2(1.f, 0.f);
             const float a = hypotf(s0.x, s0.y);
-            sa += (double)a;
-            saa += (double)a * (double)a;
-            if (i + 1 < N_block) {
+            const float ang0 = atan2f(s0.y, s0.x);
+            // the next sample's angle comes from the next lane; lane 31 computes it itself
+            float ang1 = __shfl_down_sync(0xffffffffu, ang0, 1);
+            if (lane == 31 && i + 1 < N_block) {
                 const float2 s1 = __ldg(x + i + 1);
-                const float dd = atan2f(s1.y, s1.x) - atan2f(s0.y, s0.x);
+                ang1 = atan2f(s1.y, s1.x);
+            }
+            if (in) {
+                sa += (double)a;
+                saa += (double)a * (double)a;
+            }
+            if (i + 1 < N_block) {
+                const float dd = ang1 - ang0;
                 float d = dd;
                 if (fabsf(dd) >= PI_F) {                             // np.unwrap: fold the step into (-pi, pi]
                     float m = fmodf(dd + PI_F, TWO_PI_F);
