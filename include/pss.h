@@ -84,8 +84,8 @@ typedef struct {
     float* cols;    /* [n_frames][W] rows resampled to W columns (np.interp semantics), or NULL */
     int    W;
     float* stats;   /* [n_frames][4] = max, mean, finite-min, finite-max of the row, or NULL */
-    double* moments; /* [n_frames][4] = sum I^2, sum Q^2, sum I*Q, 0 of the frame's samples, or NULL (N >= 512,
-                        N <= 8192).  A by-product of the pass that already reads the IQ: feeding it to
+    double* moments; /* [n_frames][4] = sum I^2, sum Q^2, sum I*Q, 0 of the frame's samples, or NULL (512 <= N <=
+                        65536).  A by-product of the pass that already reads the IQ: feeding it to
                         pss_demod_c64_dev_moments saves the WFM demodulator its own iq_correction pass over
                         the block (signal_processing.py:52-61 need exactly these sums). */
 } pss_psd_out;

@@ -50,8 +50,10 @@ extern "C" int pss_pipeline_c64(pss_ctx* ctx, const float* iq_host, int64_t n_bl
     if (chunk < 1) chunk = 1;
     if (chunk > n_blocks) chunk = n_blocks;
     const size_t blk_in = (size_t)io->N_block * 8;
-    const bool use_mom = io->plan && io->N_fft <= 8192;      // WFM plans consume them, others ignore them
-    if ((rc0 = pss_reserve(ctx, &ctx->p_buf[7], &ctx->p_bytes[7], (size_t)chunk * fpb * 32 + 32))) return rc0;
+    // frame moments: a by-product of the PSD pass that WFM plans consume (others ignore them); the fused PSD
+    // kernels emit them up to 65536 points.  Own slot: 7..9 are the large-transform scratch.
+    const bool use_mom = io->plan && io->N_fft <= 65536;
+    if ((rc0 = pss_reserve(ctx, &ctx->p_buf[10], &ctx->p_bytes[10], (size_t)chunk * fpb * 32 + 32))) return rc0;
     const size_t sz[7] = {
         2 * (size_t)chunk * blk_in,                         // 0 iq, two slots
         (size_t)chunk * fpb * n_bins * 4,                   // 1 db of one chunk
@@ -97,7 +99,7 @@ extern "C" int pss_pipeline_c64(pss_ctx* ctx, const float* iq_host, int64_t n_bl
         po.cols = d_cols + f0 * io->W;
         po.W = io->W;
         po.stats = d_stats + f0 * 4;
-        po.moments = use_mom ? (double*)ctx->p_buf[7] : nullptr;
+        po.moments = use_mom ? (double*)ctx->p_buf[10] : nullptr;
         if ((rc = pss_psd_c64_dev(ctx, iq_slot, io->N_fft, nf, PSS_WINDOW_HAMMING, PSS_EPI_SMOOTH_CLAMP,
                                   PSS_PREC_FP64, &po)))
             return rc;
@@ -107,7 +109,7 @@ extern "C" int pss_pipeline_c64(pss_ctx* ctx, const float* iq_host, int64_t n_bl
             return rc;
         if (io->plan)
             if ((rc = pss_demod_c64_dev_moments(ctx, io->plan, iq_slot, nb, d_audio + (size_t)b0 * out_len * ch,
-                                                use_mom ? (const double*)ctx->p_buf[7] : nullptr, fpb)))
+                                                use_mom ? (const double*)ctx->p_buf[10] : nullptr, fpb)))
                 return rc;
         PSS_CUDA(ctx, cudaEventRecord(ps->in_free[slot], st));
         PSS_CUDA(ctx, cudaEventRecord(ps->done, st));

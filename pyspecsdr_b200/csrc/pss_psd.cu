@@ -868,6 +868,7 @@ struct PsdLargeParams {
     cx<double>* Y;                 // [grid][N] scratch
     float* rawdb;                  // [grid][N] scratch (EPI_SMOOTH)
     float* srow2;                  // [grid][N] scratch (EPI_SMOOTH, rows that do not fit shared memory)
+    double* moments;               // [n_frames][4] sum I^2, Q^2, IQ per frame (by-product for the WFM demod), or null
 };
 
 template <int LOG2N, int EPI>
@@ -880,6 +881,7 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
     __shared__ float cand[64];
     __shared__ double dsum_s[16];
     __shared__ float fmx_s[16], fmn_s[16];
+    __shared__ double mom_s[16][3];
     const int tid = threadIdx.x, g = tid >> 8, t = tid & 255, lane = tid & 31, warp = tid >> 5;
     cx<double>* buf = reinterpret_cast<cx<double>*>(smem_raw) + (size_t)g * fft_padded(N2);
     const HalfBarrier hbar{1 + g};
@@ -897,6 +899,7 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
             if (tid < 2) ub[tid] = tid == 0 ? 0xffffffffu : 0u;      // raw-row bounds (keys)
         }
         const float2* src = p.iq + frame * N;
+        float mii = 0.f, mqq = 0.f, miq = 0.f;
 #pragma unroll(N1 == 4 ? 4 : N1 == 8 ? 2 : 1)
         for (int c = 0; c < N2 / 512; ++c) {
             const int n2 = tid + 512 * c;
@@ -904,6 +907,11 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
 #pragma unroll
             for (int n1 = 0; n1 < N1; ++n1) {
                 const float2 s = __ldcs(src + n2 + N2 * n1);
+                if constexpr (EPI == EPI_SMOOTH) {
+                    mii = fmaf(s.x, s.x, mii);
+                    mqq = fmaf(s.y, s.y, mqq);
+                    miq = fmaf(s.x, s.y, miq);
+                }
                 if (p.window) {
                     const double w = __ldg(p.window + n2 + N2 * n1);
                     v[n1] = {(double)s.x * w, (double)s.y * w};
@@ -921,7 +929,34 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
             for (int k1 = 0; k1 < N1; ++k1)
                 st_keep(reinterpret_cast<double2*>(Y + k1 * N2 + n2), o[k1].x, o[k1].y, keep);
         }
+        if constexpr (EPI == EPI_SMOOTH) {
+            if (p.moments) {              // float partials per thread / warp, fp64 across the frame
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    mii += __shfl_xor_sync(0xffffffffu, mii, o);
+                    mqq += __shfl_xor_sync(0xffffffffu, mqq, o);
+                    miq += __shfl_xor_sync(0xffffffffu, miq, o);
+                }
+                if (lane == 0) {
+                    mom_s[warp][0] = (double)mii;
+                    mom_s[warp][1] = (double)mqq;
+                    mom_s[warp][2] = (double)miq;
+                }
+            }
+        }
         __syncthreads();
+        if constexpr (EPI == EPI_SMOOTH) {
+            if (p.moments && tid == 0) {
+                double a = 0.0, b = 0.0, c = 0.0;
+                for (int w = 0; w < 16; ++w) {
+                    a += mom_s[w][0];
+                    b += mom_s[w][1];
+                    c += mom_s[w][2];
+                }
+                double* m = p.moments + frame * 4;
+                m[0] = a; m[1] = b; m[2] = c; m[3] = 0.0;
+            }
+        }
         if constexpr (LOG2N == 14) {
             // pull the next frame of this CTA into L2 while the row transforms keep the fp64 pipe busy
             // (measured: -4 % at 16384 points; at 32768+ the scratch already fills the L2 and it hurts)
@@ -1239,6 +1274,7 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
         lp.cols = out->cols;
         lp.W = out->W;
         lp.stats = out->stats;
+        lp.moments = smooth ? out->moments : nullptr;
         lp.Y = (cx<double>*)ctx->p_buf[7];
         if (smooth) {
             if ((rc = pss_reserve(ctx, &ctx->p_buf[9], &ctx->p_bytes[9], (size_t)grid * N * 4))) return rc;
@@ -1341,7 +1377,7 @@ extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_f
     if (precision != PSS_PREC_FP64 && precision != PSS_PREC_FP32) return PSS_ERR_ARG;
     if (epilogue == PSS_EPI_RAW && !out->db) return PSS_ERR_ARG;
     if (epilogue == PSS_EPI_RAW && (out->cols || out->stats || out->moments)) return PSS_ERR_UNSUPPORTED;
-    if (out->moments && N > 8192) return PSS_ERR_UNSUPPORTED;
+    if (out->moments && N > 65536) return PSS_ERR_UNSUPPORTED;
     if (out->cols && out->W < 1) return PSS_ERR_ARG;
     const int log2n = ilog2_exact(N);
     if (log2n < 0) return PSS_ERR_UNSUPPORTED;

@@ -118,12 +118,13 @@ def test_wfm_with_psd_moments_matches_oracle(ctx):
     skips its own iq_correction pass; audio must stay within tolerance (pipeline path)."""
     fs, n = 2.4e6, 32768
     x = np.stack([synth.make("wbfm", n, seed=70 + s) * np.complex64(0.9 + 0.05j) for s in range(5)]).astype(np.complex64)
-    out = ctx.pipeline(x, fs, "WFM", n_fft=4096, W=64)
     alone = ctx.demod(x, fs, "WFM")
-    for f in range(len(x)):
-        ref = O.demod(x[f], fs, "WFM")
-        assert rms(out["audio"][f], ref) <= TOL_RMS
-        assert rms(out["audio"][f], alone[f].astype(np.float64)) <= 1e-6
+    for n_fft in (4096, 16384, 32768):        # 32768 = the app's default: the whole read is one FFT frame
+        out = ctx.pipeline(x, fs, "WFM", n_fft=n_fft, W=64)
+        for f in range(len(x)):
+            ref = O.demod(x[f], fs, "WFM")
+            assert rms(out["audio"][f], ref) <= TOL_RMS, n_fft
+            assert rms(out["audio"][f], alone[f].astype(np.float64)) <= 1e-6, n_fft
 
 
 @pytest.mark.parametrize("mode", ["AM", "USB", "LSB"])
