@@ -1209,7 +1209,11 @@ template <int LOG2N, int EPI>
 static int launch_large_fused(pss_ctx* ctx, const PsdLargeParams& p, unsigned grid) {
     auto kern = psd_large_kernel<LOG2N, EPI>;
     constexpr int SMEM = 2 * fft_padded(4096) * (int)sizeof(cx<double>);
-    PSS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    static bool configured[16] = {};
+    if (!configured[ctx->device & 15]) {
+        PSS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+        configured[ctx->device & 15] = true;
+    }
     kern<<<grid, 512, SMEM, ctx->stream>>>(p);
     PSS_LAUNCH_CHECK(ctx);
     return PSS_OK;
