@@ -156,7 +156,7 @@ def test_bandpass_filter_long_row(ctx):
 @pytest.mark.parametrize("mode", ["NFM", "WFM"])
 def test_decimating_demod_rate_extremes(ctx, mode, fs, n):
     """Low rates x long reads (more than 4096 audio samples per block: un-normalised outputs and state slots
-    live in the CTA's L2 slice) and very high rates (q > 1600: 8-chunk tiles), tools/probe_rates.py."""
+    live in the CTA's L2 slice) and very high rates (q > 1600: 8-chunk tiles), tests/tools/probe_rates.py."""
     import warnings
     x = synth.wbfm(n, seed=6, fs=fs, dev=min(75e3, fs / 8))
     try:

@@ -88,6 +88,13 @@ def test_no_gpu_means_loud_failure_not_fallback():
         core.Context(0)
 
 
+def test_tools_never_import_oracle():
+    # only tests/ (incl. tests/tools), __graft_entry__.smoke() and bench.py's CPU arms may touch oracle/
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            assert "oracle" not in open(os.path.join(ROOT, "tools", f)).read(), f
+
+
 def test_product_package_never_imports_oracle():
     pkg = os.path.join(ROOT, "pyspecsdr_b200")
     for dirpath, _, files in os.walk(pkg):
@@ -172,7 +179,7 @@ def test_tools_and_bench_compile():
     B200 box, a syntax error there costs a gpurun call."""
     import glob
     import py_compile
-    files = sorted(glob.glob(os.path.join(ROOT, "tools", "*.py"))) + [os.path.join(ROOT, "bench.py"),
+    files = sorted(glob.glob(os.path.join(ROOT, "tools", "*.py")) + glob.glob(os.path.join(ROOT, "tests", "tools", "*.py"))) + [os.path.join(ROOT, "bench.py"),
                                                                         os.path.join(ROOT, "__graft_entry__.py")]
     assert len(files) >= 8
     for f in files:

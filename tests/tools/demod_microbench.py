@@ -1,6 +1,6 @@
 """Scratch micro-benchmark of the demodulation kernels (device-resident input, CUDA events)."""
 import json, os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 import torch
 from pyspecsdr_b200 import core

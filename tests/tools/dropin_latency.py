@@ -2,7 +2,7 @@
 oracle port of the reference functions on one host core.  Prints a small table."""
 import os, sys, time, warnings
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from pyspecsdr_b200 import signal_processing as sp, synth
 from oracle import ref_dsp as O
 

@@ -1,7 +1,7 @@
 """Every (sample rate, block size, mode) combination a user can plausibly select, against the oracle."""
 import os, sys, warnings
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from pyspecsdr_b200 import core, synth
 from oracle import ref_dsp as O
 ctx = core.Context(0)

@@ -1,5 +1,5 @@
 import sys, numpy as np, warnings
-import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from pyspecsdr_b200 import core, synth
 from oracle import ref_dsp as O
 ctx = core.Context(0)
