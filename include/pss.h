@@ -16,7 +16,15 @@
  *    return when the result is in the caller's buffer.
  *  - the caller owns every buffer; the library owns only the context (stream, window/twiddle
  *    tables, filter tables, scratch, display history rings).
- *  - one context per thread / per GPU.  Calls on one context are stream-ordered.
+ *  - one context per thread / per GPU.  Calls on one context are stream-ordered.  Everything the library
+ *    allocates (tables, scratch, pipeline streams and events, display rings) belongs to a context and is
+ *    released by pss_destroy; two contexts on one GPU share nothing.
+ *  - every struct that crosses the ABI starts with `size_t struct_size`, which the caller sets to
+ *    sizeof(the struct) as compiled; a mismatch (a binding built against another header revision) is
+ *    rejected with PSS_ERR_ARG instead of reading past the caller's struct.
+ *  - stream contract of the *_dev variants: inputs must be complete on, and outputs are produced on, the
+ *    context's stream (pss_set_stream adopts the caller's; with the context's own stream the caller orders
+ *    its producers before the call and calls pss_sync before consuming).
  */
 #ifndef PSS_H
 #define PSS_H
@@ -44,7 +52,6 @@ enum { PSS_EPI_RAW = 0, PSS_EPI_SMOOTH_CLAMP = 1 };
 enum { PSS_PREC_FP64 = 0, PSS_PREC_FP32 = 1 };
 enum { PSS_MODE_NFM = 0, PSS_MODE_WFM = 1, PSS_MODE_AM = 2, PSS_MODE_USB = 3, PSS_MODE_LSB = 4,
        PSS_MODE_RAW = 5 };
-enum { PSS_DISPLAY_WATERFALL = 0, PSS_DISPLAY_PERSISTENCE = 1 };
 
 /* ------------------------------------------------------------------ lifetime / plumbing */
 int         pss_init(int device, pss_ctx** out);
@@ -80,6 +87,7 @@ void        pss_host_free(void* p);
  * selected implicitly.
  */
 typedef struct {
+    size_t struct_size; /* = sizeof(pss_psd_out) */
     float* db;      /* [n_frames][n_out] dB rows, or NULL */
     float* cols;    /* [n_frames][W] rows resampled to W columns (np.interp semantics), or NULL */
     int    W;
@@ -96,10 +104,14 @@ int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, int 
                     int epilogue, int precision, const pss_psd_out* out);
 
 /* ------------------------------------------------------------------ scanner
- * Replaces the per-step numerics of the 'c'-key scan loop pyspecsdr.py:2542-2552 and of
- * scan_frequencies pyspecsdr.py:1050-1057: un-windowed FFT -> dB -> peak -> number of bins above
- * (peak - rel_db) [use_abs = 0, the inline loop: rel_db = 20] or above abs threshold `thr_db`
- * [use_abs = 1, scan_frequencies].  bandwidth = count * fs / N is left to the caller.
+ * Replaces the per-step numerics of the 'c'-key scan loop pyspecsdr.py:2542-2552: un-windowed FFT -> dB ->
+ * peak -> number of bins above (peak - rel_db) [use_abs = 0, the inline loop: rel_db = 20], or above an
+ * absolute threshold `thr_db` [use_abs = 1: the mask of scan_frequencies pyspecsdr.py:1050-1057; that
+ * function itself reads 0.1 s * fs samples per step, which is not a power of two, so only its mask rule
+ * is offered here, on power-of-two reads].  512 <= N <= 8192, a power of two.
+ * bandwidth = count * fs / N is left to the caller.
+ * The count is INTEGER output and is taken in the fp64 power domain (|X|^2 + 1e-10 > p_max * 10^(-rel/10)),
+ * which equals the reference's dB comparison except on ties at the 1e-15 level.
  * db_rows (optional) receives the N-bin dB row of every step (the wide-band "stitch").
  */
 int pss_scan_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_steps, int use_abs, float thr_db,
@@ -111,21 +123,14 @@ int pss_scan_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_steps, int 
  * of the row (np.percentile, linear interpolation), display range [floor - 0.1*span, max + 0.05*span],
  * clip to [0,1], ** 0.7, W-column np.interp resample.  db [n_frames][n_bins] (host), cols [n_frames][W],
  * range [n_frames][2] = display_min, display_max (may be NULL).
- * (draw_surface_plot :1575-1596 needs no kernel of its own: it is pss_display_render with rows_max = 1,
- *  guard_zero_range = 1, followed by int(v * 20).) */
+ * (draw_surface_plot :1575-1596 is a display stream of kind PSS_QUANT_SURFACE, see "display accumulate".) */
 int pss_spectrum_normalise(pss_ctx* ctx, const float* db, int n_bins, int64_t n_frames, int W, float* cols,
                            float* range);
-
-/* Glyph / colour index planes of the draw_* functions from normalised values
- * (pss_display_render output), so the TUI can paint one string per row instead of a Python loop per
- * cell.  kind: WATERFALL  a = glyph level 0..3 ('.', '-', '=', '#'; pyspecsdr.py:1390-1397), b = int(v*5) (:1388)
- *             GRADIENT   a = int(v*8) index into ' ._-=+*#@' (:1691),            b = int(v*5) (:1695)
- *             PERSISTENCE a = screen row int((1-v)*(H-1)) (:1556)               b = int(v*5)
- *             SURFACE    a = magnitude int(v*20) (:1593)                         b = int(v*5)
- * NaN inputs (rows older than the history) give 255.  plane_b may be NULL. */
-enum { PSS_QUANT_WATERFALL = 0, PSS_QUANT_GRADIENT = 1, PSS_QUANT_PERSISTENCE = 2, PSS_QUANT_SURFACE = 3 };
-int pss_display_quantise(pss_ctx* ctx, const float* norm, int64_t n, int kind, int H, uint8_t* plane_a,
-                         uint8_t* plane_b);
+/* The same on HOST fp64 rows, fp64 throughout in numpy's operation order (percentile virtual index, lerp,
+ * clip, pow, np.interp without fused multiply-add): the bar heights int(value * display_height) match the
+ * reference's wherever CUDA's and the host libm's pow() agree to the last bit. */
+int pss_spectrum_normalise_f64(pss_ctx* ctx, const double* db, int n_bins, int64_t n_frames, int W, double* cols,
+                               double* range);
 
 /* ------------------------------------------------------------------ demodulation
  * Replaces demodulate_signal(samples, sample_rate, mode)  signal_processing.py:220-240 and the
@@ -152,6 +157,7 @@ int pss_display_quantise(pss_ctx* ctx, const float* norm, int64_t n, int kind, i
 enum { PSS_PLAN_DECIM = 0, PSS_PLAN_FIR = 1, PSS_PLAN_SOS = 2, PSS_PLAN_RAW = 3 };
 
 typedef struct {
+    size_t struct_size;    /* = sizeof(pss_demod_desc) */
     int kind;              /* PSS_PLAN_* */
     int mode;              /* PSS_MODE_* */
     int N;                 /* IQ samples per block */
@@ -159,6 +165,9 @@ typedef struct {
     int q, n_out, lead, SF, SB, n_body, m_tail, tail_start, tail_len;
     int scan_block_f, scan_block_b;     /* block lengths of the forward / backward state scans */
     float scale, norm;
+    int iq_correct;        /* WFM plans: 1 = iq_correction (signal_processing.py:46-80) fused in front of the
+                              discriminator, which is what demodulate_signal does (:222-225); 0 = none, which
+                              is demodulate_wfm called directly (:119-176) */
     const double* body;    /* [(SF+SB+1)][q+lead] response tables of one body chunk */
     const double* AF;      /* [SF][SF]   forward state transition over one chunk */
     const double* AFB;     /* [SF][SF]   AF ^ scan_block_f */
@@ -183,40 +192,86 @@ typedef struct pss_demod_plan pss_demod_plan;
 
 int  pss_demod_plan_create(pss_ctx* ctx, const pss_demod_desc* desc, pss_demod_plan** out);
 void pss_demod_plan_destroy(pss_ctx* ctx, pss_demod_plan* plan);
-/* Samples written per block and channel count of a plan's output. */
+/* Samples written per block and channel count of a plan's output; IQ samples per block it was built for. */
 int  pss_demod_plan_out_len(const pss_demod_plan* plan);
+int  pss_demod_plan_block_len(const pss_demod_plan* plan);
 int  pss_demod_plan_channels(const pss_demod_plan* plan);
 int  pss_demod_c64(pss_ctx* ctx, pss_demod_plan* plan, const float* iq, int64_t n_frames, float* audio);
 int  pss_demod_c64_dev(pss_ctx* ctx, pss_demod_plan* plan, const float* iq, int64_t n_frames,
                        float* audio);
 /* As pss_demod_c64_dev, with the I/Q second moments of every block supplied as `frames_per_block`
- * consecutive rows of a PSD call's `moments` output over the same IQ (device pointer).  Used by WFM
- * plans (iq_correction); ignored by the others. */
+ * consecutive rows of a PSD call's `moments` output over the same IQ (device pointer), each row covering
+ * `frame_len` samples; frames_per_block * frame_len must equal the plan's block length (PSS_ERR_ARG
+ * otherwise).  Used by WFM plans (iq_correction); ignored by the others. */
 int  pss_demod_c64_dev_moments(pss_ctx* ctx, pss_demod_plan* plan, const float* iq, int64_t n_frames,
-                               float* audio, const double* moments, int frames_per_block);
+                               float* audio, const double* moments, int frames_per_block, int frame_len);
 
 /* ------------------------------------------------------------------ display accumulate
  * Replaces the numeric part of draw_waterfall (pyspecsdr.py:1351-1358, 1373-1398),
- * draw_gradient_waterfall (:1649-1696) and draw_persistence (:1521-1556): a history of the last
- * `rows_max` dB rows (30 waterfall / 10 persistence), finite min/max over the whole stack, every
- * row resampled to W columns with np.interp semantics, normalised (v - min) / (max - min).
+ * draw_gradient_waterfall (:1649-1696), draw_persistence (:1521-1556) and draw_surface_plot (:1575-1596):
+ * a history of the last `rows_max` dB rows (WATERFALL_MAX_LINES = 30, PERSISTENCE_LENGTH = 10, :131, :152),
+ * finite min/max over the whole stack, every row resampled to W columns with np.interp semantics,
+ * normalised (v - min) / (max - min), then the per-cell int() quantisation.
  *
- * The history is not a separate ring: the PSD kernel already leaves every row's W-column resample
- * (`cols`) and finite min/max (`stats`) in device memory in frame order, so the history of frame t
- * is simply frames t, t-1, ..., t-rows_max+1 of those arrays.  Render r (0 <= r < n_renders) draws
- * the display as it stands after frame  t = first + r*step.
- *   norm   [n_renders][rows_max][W]  newest row first (the order draw_waterfall walks
- *                                    reversed(WATERFALL_HISTORY)); rows older than frame 0 are NaN
- *   minmax [n_renders][2]            stack min, max
- *   guard_zero_range: 0 = waterfall (divide by max-min as is), 1 = gradient / persistence
- *                     (range 0 is replaced by 1, pyspecsdr.py:1528-1530, 1657-1659)
+ * STATEFUL form (what the reference's global WATERFALL_HISTORY / PERSISTENCE_HISTORY lists are): a context
+ * owns any number of display streams, each a ring of the last rows_max - 1 rows (their W-column resample and
+ * finite min/max) carried on the device across calls, so N calls of one row are bitwise one call of N rows.
+ *   pss_display_open(ctx, stream, kind, W, rows_max, H)   create / reset stream `stream` (any int id)
+ *        kind = PSS_QUANT_*: WATERFALL divides by max-min as is; GRADIENT / PERSISTENCE / SURFACE replace a
+ *        zero range by 1 (:1528-1530, :1657-1659, :1577-1579).  H = display_height (PERSISTENCE only).
+ *        SURFACE has no history (rows_max must be 1).
+ *   pss_display_accumulate_f64   HOST fp64 dB rows [n_rows][n_bins], one render after every row (the call
+ *        pattern of the draw_* functions).  Everything is fp64 in numpy's operation order with no fused
+ *        multiply-add, so the planes are bit-identical to what the reference draws from the same rows.
+ *   pss_display_accumulate_dev   DEVICE float32 rows as the PSD kernel leaves them (`cols`, `stats` of
+ *        pss_psd_out, frame order = time order); render r shows the display as it stands after frame
+ *        first + r*step of this call.  Asynchronous on the context's stream.
+ * Outputs (any may be NULL), newest row first (the order draw_waterfall walks reversed(WATERFALL_HISTORY));
+ * rows beyond the history are NaN / 255:
+ *   norm / norm64 [n_renders][rows_max][W]   minmax / minmax64 [n_renders][2] stack min, max
+ *   n_rows [n_renders]                       rows in the history at each render
+ *   plane_a, plane_b [n_renders][rows_max][W] uint8:
+ *     WATERFALL    a = glyph level 0..3 ('.', '-', '=', '#'; :1390-1397)   b = int(v*5) colour index (:1388)
+ *     GRADIENT     a = int(v*8) index into ' ._-=+*#@' (:1691)             b = int(v*5) (:1695)
+ *     PERSISTENCE  a = screen row int((1-v)*(H-1)), 255 if outside [0,H) (:1556-1557)
+ *                  b = colour pair of the trace int(1 + 5*(1 - 0.7**(rows_max - i))) (:1544-1545)
+ *     SURFACE      a = magnitude int(v*20) (:1593)                          b = int(v*5)
+ *   (accumulate_f64 fills norm, norm64, minmax64, n_rows and the planes; accumulate_dev fills norm, minmax,
+ *    n_rows and the planes.)
  */
+enum { PSS_QUANT_WATERFALL = 0, PSS_QUANT_GRADIENT = 1, PSS_QUANT_PERSISTENCE = 2, PSS_QUANT_SURFACE = 3 };
+
+typedef struct {
+    size_t   struct_size;   /* = sizeof(pss_display_out) */
+    float*   norm;
+    float*   minmax;
+    double*  norm64;
+    double*  minmax64;
+    uint8_t* plane_a;
+    uint8_t* plane_b;
+    int32_t* n_rows;
+} pss_display_out;
+
+int pss_display_open(pss_ctx* ctx, int stream, int kind, int W, int rows_max, int H);
+int pss_display_close(pss_ctx* ctx, int stream);
+int pss_display_rows(const pss_ctx* ctx, int stream);     /* rows carried in the ring (< rows_max), or < 0 */
+int pss_display_accumulate_f64(pss_ctx* ctx, int stream, const double* rows, int n_bins, int64_t n_rows,
+                               const pss_display_out* out);
+int pss_display_accumulate_dev(pss_ctx* ctx, int stream, const float* cols, const float* stats, int64_t n_frames,
+                               int64_t first, int64_t step, int64_t n_renders, const pss_display_out* out);
+
+/* STATELESS form: the history of frame t is frames t, t-1, ..., t-rows_max+1 of one call's `cols` / `stats`
+ * arrays.  guard_zero_range: 0 = waterfall, 1 = gradient / persistence. */
 int pss_display_render_dev(pss_ctx* ctx, const float* cols, const float* stats, int W, int64_t n_frames,
                            int rows_max, int64_t first, int64_t step, int64_t n_renders,
                            int guard_zero_range, float* norm, float* minmax);
 int pss_display_render(pss_ctx* ctx, const float* cols, const float* stats, int W, int64_t n_frames,
                        int rows_max, int64_t first, int64_t step, int64_t n_renders,
                        int guard_zero_range, float* norm, float* minmax);
+
+/* Glyph / colour planes from already-normalised float32 values (same quantisation rules as above). */
+int pss_display_quantise(pss_ctx* ctx, const float* norm, int64_t n, int kind, int H, uint8_t* plane_a,
+                         uint8_t* plane_b);
 
 /* ------------------------------------------------------------------ whole main-loop iteration, batched
  * One call = what pyspecsdr.py's main loop does per SDR read (pyspecsdr.py:2236-2283 plus the
@@ -229,11 +284,19 @@ int pss_display_render(pss_ctx* ctx, const float* cols, const float* stats, int 
  *   audio  [n_blocks][out_len][channels]          cols   [n_blocks*fpb][W]     (fpb = N_block / N_fft)
  *   stats  [n_blocks*fpb][4]                      db     [n_blocks*fpb][N_fft-4]
  *   norm   [n_blocks][rows_max][W]                minmax [n_blocks][2]
+ * The call uses its own copy/compute streams and events (owned by the context) and returns when every
+ * output is in the caller's buffers.
  */
 typedef struct {
+    size_t struct_size;            /* = sizeof(pss_pipeline_io) */
     int N_block, N_fft, W, rows_max;
-    pss_demod_plan* plan;          /* NULL = no demodulation */
+    pss_demod_plan* plan;          /* NULL = no demodulation; must have been created for N = N_block */
     float *audio, *cols, *stats, *db, *norm, *minmax;
+    int display_stream;            /* < 0: the waterfall history starts empty at the first block of the call;
+                                      >= 0: a stream from pss_display_open(ctx, id, kind, W, rows_max, H): the
+                                      history is carried across calls (one call of N blocks == N calls of one) */
+    uint8_t *plane_a, *plane_b;    /* [n_blocks][rows_max][W] glyph / colour planes of the stream's kind
+                                      (display_stream >= 0 only), or NULL */
 } pss_pipeline_io;
 
 int pss_pipeline_c64(pss_ctx* ctx, const float* iq_host, int64_t n_blocks, const pss_pipeline_io* io);
@@ -244,6 +307,9 @@ int pss_pipeline_c64(pss_ctx* ctx, const float* iq_host, int64_t n_blocks, const
  *                                                        signal_processing.py:34-42  (sos designed by caller)
  * pss_power_c64        measure_signal_power(samples)     signal_processing.py:325-328 -> dB per block
  * pss_audio_to_int16   np.int16(samples * 32767)         audio_processing.py:36-38, io_manager.py:25-26
+ *                      on float32 samples (the library's wire format)
+ * pss_audio_to_int16_f64  the same on the float64 array the reference holds at that line: one fp64 product
+ *                      and the truncating cast, bit-identical to numpy's
  * Host pointers in and out.
  */
 int pss_iq_correct_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, float* out);
@@ -251,6 +317,7 @@ int pss_sosfilt_f32(pss_ctx* ctx, const float* x, int N, int64_t n_frames, const
                     float* y);
 int pss_power_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, float* power_db);
 int pss_audio_to_int16(pss_ctx* ctx, const float* audio, int64_t n, int16_t* pcm);
+int pss_audio_to_int16_f64(pss_ctx* ctx, const double* audio, int64_t n, int16_t* pcm);
 
 /* ------------------------------------------------------------------ signal classifier
  * classify_signal(samples, sample_rate, bandwidth), signal_processing.py:296-322: Welch PSD (scipy.signal.welch

@@ -16,20 +16,34 @@ class PssError(RuntimeError):
     pass
 
 
-class PsdOut(C.Structure):
-    _fields_ = [("db", C.c_void_p), ("cols", C.c_void_p), ("W", C.c_int), ("stats", C.c_void_p),
-                ("moments", C.c_void_p)]
+class _Sized(C.Structure):
+    """Every ABI struct starts with `size_t struct_size` = sizeof(struct); set here at construction."""
+
+    def __init__(self, *args, **kw):
+        super().__init__(C.sizeof(type(self)), *args, **kw)
 
 
-class DemodDesc(C.Structure):
+class PsdOut(_Sized):
+    """Mirror of pss_psd_out (include/pss.h)."""
+    _fields_ = [("struct_size", C.c_size_t), ("db", C.c_void_p), ("cols", C.c_void_p), ("W", C.c_int),
+                ("stats", C.c_void_p), ("moments", C.c_void_p)]
+
+
+class DisplayOut(_Sized):
+    """Mirror of pss_display_out (include/pss.h)."""
+    _fields_ = [("struct_size", C.c_size_t), ("norm", C.c_void_p), ("minmax", C.c_void_p), ("norm64", C.c_void_p),
+                ("minmax64", C.c_void_p), ("plane_a", C.c_void_p), ("plane_b", C.c_void_p), ("n_rows", C.c_void_p)]
+
+
+class DemodDesc(_Sized):
     """Mirror of pss_demod_desc (include/pss.h)."""
     _dp = C.POINTER(C.c_double)
     _fields_ = [
-        ("kind", C.c_int), ("mode", C.c_int), ("N", C.c_int),
+        ("struct_size", C.c_size_t), ("kind", C.c_int), ("mode", C.c_int), ("N", C.c_int),
         ("q", C.c_int), ("n_out", C.c_int), ("lead", C.c_int), ("SF", C.c_int), ("SB", C.c_int),
         ("n_body", C.c_int), ("m_tail", C.c_int), ("tail_start", C.c_int), ("tail_len", C.c_int),
         ("scan_block_f", C.c_int), ("scan_block_b", C.c_int),
-        ("scale", C.c_float), ("norm", C.c_float),
+        ("scale", C.c_float), ("norm", C.c_float), ("iq_correct", C.c_int),
         ("body", _dp), ("AF", _dp), ("AFB", _dp), ("AB", _dp), ("ABB", _dp), ("MB", _dp), ("CR", _dp),
         ("CB", _dp), ("DB", C.c_double), ("head", _dp), ("tail_T", _dp), ("tail_M", _dp),
         ("taps", _dp), ("n_taps", C.c_int),
@@ -37,11 +51,12 @@ class DemodDesc(C.Structure):
     ]
 
 
-class PipelineIO(C.Structure):
+class PipelineIO(_Sized):
     """Mirror of pss_pipeline_io (include/pss.h)."""
-    _fields_ = [("N_block", C.c_int), ("N_fft", C.c_int), ("W", C.c_int), ("rows_max", C.c_int),
-                ("plan", C.c_void_p), ("audio", C.c_void_p), ("cols", C.c_void_p), ("stats", C.c_void_p),
-                ("db", C.c_void_p), ("norm", C.c_void_p), ("minmax", C.c_void_p)]
+    _fields_ = [("struct_size", C.c_size_t), ("N_block", C.c_int), ("N_fft", C.c_int), ("W", C.c_int),
+                ("rows_max", C.c_int), ("plan", C.c_void_p), ("audio", C.c_void_p), ("cols", C.c_void_p),
+                ("stats", C.c_void_p), ("db", C.c_void_p), ("norm", C.c_void_p), ("minmax", C.c_void_p),
+                ("display_stream", C.c_int), ("plane_a", C.c_void_p), ("plane_b", C.c_void_p)]
 
 
 def _signatures():
@@ -72,14 +87,22 @@ def _signatures():
         "pss_classify_c64": (i32, [vp, vp, i32, i64, C.c_double, vp, vp]),
         "pss_classify_c64_dev": (i32, [vp, vp, i32, i64, C.c_double, vp, vp]),
         "pss_display_quantise": (i32, [vp, vp, i64, i32, i32, vp, vp]),
+        "pss_display_open": (i32, [vp, i32, i32, i32, i32, i32]),
+        "pss_display_close": (i32, [vp, i32]),
+        "pss_display_rows": (i32, [vp, i32]),
+        "pss_display_accumulate_f64": (i32, [vp, i32, vp, i32, i64, C.POINTER(DisplayOut)]),
+        "pss_display_accumulate_dev": (i32, [vp, i32, vp, vp, i64, i64, i64, i64, C.POINTER(DisplayOut)]),
         "pss_spectrum_normalise": (i32, [vp, vp, i32, i64, i32, vp, vp]),
+        "pss_spectrum_normalise_f64": (i32, [vp, vp, i32, i64, i32, vp, vp]),
+        "pss_audio_to_int16_f64": (i32, [vp, vp, i64, vp]),
+        "pss_demod_plan_block_len": (i32, [vp]),
         "pss_demod_plan_create": (i32, [vp, C.POINTER(DemodDesc), C.POINTER(vp)]),
         "pss_demod_plan_destroy": (None, [vp, vp]),
         "pss_demod_plan_out_len": (i32, [vp]),
         "pss_demod_plan_channels": (i32, [vp]),
         "pss_demod_c64": (i32, [vp, vp, vp, i64, vp]),
         "pss_demod_c64_dev": (i32, [vp, vp, vp, i64, vp]),
-        "pss_demod_c64_dev_moments": (i32, [vp, vp, vp, i64, vp, vp, i32]),
+        "pss_demod_c64_dev_moments": (i32, [vp, vp, vp, i64, vp, vp, i32, i32]),
     }
 
 

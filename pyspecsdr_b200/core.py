@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib, filters
-from ._lib import DemodDesc, PipelineIO, PsdOut, PssError, lib
+from ._lib import DemodDesc, DisplayOut, PipelineIO, PsdOut, PssError, lib
 
 WINDOWS = {"none": 0, "hamming": 1, "hann": 2, None: 0}
 
@@ -38,7 +38,7 @@ def _dp(a: np.ndarray):
 class DemodPlan:
     """Device-resident filter tables for one (mode, sample_rate, block length)."""
 
-    def __init__(self, ctx: "Context", mode: str, fs: float, N: int):
+    def __init__(self, ctx: "Context", mode: str, fs: float, N: int, iq_correct: bool = True):
         self.ctx, self.mode, self.fs, self.N = ctx, mode, float(fs), int(N)
         desc = DemodDesc()
         if mode not in filters.MODES:
@@ -61,6 +61,7 @@ class DemodPlan:
             desc.scan_block_f = max(1, -(-p.n_body // (256 // p.SF)))
             desc.scan_block_b = max(1, -(-p.n_body // (256 // p.SB)))
             desc.scale, desc.norm, desc.DB = np.float32(p.scale), p.norm, p.DB
+            desc.iq_correct = 1 if (mode == "WFM" and iq_correct) else 0
             desc.body, desc.AF, desc.AB, desc.MB = arr(p.body), arr(p.AF), arr(p.AB), arr(p.MB)
             desc.AFB = arr(filters.matrix_power_seq(p.AF, desc.scan_block_f))
             desc.ABB = arr(filters.matrix_power_seq(p.AB, desc.scan_block_b))
@@ -99,6 +100,7 @@ class Context:
         self._h = h
         self.device = device
         self._plans = {}
+        self._streams = {}
 
     # ------------------------------------------------------------------ plumbing
     def close(self):
@@ -182,30 +184,36 @@ class Context:
                                       _ptr(rows)), "pss_scan_c64_dev")
 
     # ------------------------------------------------------------------ demodulation
-    def demod_plan(self, mode: str, fs: float, N: int) -> DemodPlan:
-        key = (mode, float(fs), int(N))
+    def demod_plan(self, mode: str, fs: float, N: int, iq_correct: bool = True) -> DemodPlan:
+        """`iq_correct` (WFM only): True = demodulate_signal's chain (iq_correction fused into the kernel),
+        False = demodulate_wfm called directly on whatever the caller passes."""
+        key = (mode, float(fs), int(N), bool(iq_correct) or mode != "WFM")
         if key not in self._plans:
-            self._plans[key] = DemodPlan(self, mode, fs, N)
+            self._plans[key] = DemodPlan(self, mode, fs, N, iq_correct)
         return self._plans[key]
 
-    def demod(self, samples, fs: float, mode: str) -> np.ndarray:
+    def demod(self, samples, fs: float, mode: str, iq_correct: bool = True) -> np.ndarray:
         """Batched demodulate_signal for one mode.  Returns float32 [F, out_len, channels]
         (channels = 2 for NFM/WFM, 1 for AM/USB/LSB/RAW)."""
         x = _as_frames(samples)
         F, N = x.shape
-        plan = self.demod_plan(mode, fs, N)
+        plan = self.demod_plan(mode, fs, N, iq_correct)
         out = np.empty((F, plan.out_len, plan.channels), np.float32)
         self._ck(lib.pss_demod_c64(self._h, plan._h, x.ctypes.data, F, out.ctypes.data), f"pss_demod_c64({mode})")
         return out
 
     def demod_dev(self, plan: DemodPlan, iq, n_frames: int, audio, moments=None, frames_per_block=0):
         """Device-pointer demodulation.  `moments` = the PSD call's per-frame I/Q moments over the same
-        IQ (frames_per_block rows per block): lets a WFM plan skip its own iq_correction pass."""
+        IQ (frames_per_block rows per block, each over N / frames_per_block samples): lets a WFM plan skip
+        its own iq_correction pass."""
         if moments is None:
             self._ck(lib.pss_demod_c64_dev(self._h, plan._h, _ptr(iq), n_frames, _ptr(audio)), "pss_demod_c64_dev")
         else:
+            if frames_per_block < 1 or plan.N % frames_per_block:
+                raise ValueError("frames_per_block must divide the plan's block length")
             self._ck(lib.pss_demod_c64_dev_moments(self._h, plan._h, _ptr(iq), n_frames, _ptr(audio), _ptr(moments),
-                                                   frames_per_block), "pss_demod_c64_dev_moments")
+                                                   frames_per_block, plan.N // frames_per_block),
+                     "pss_demod_c64_dev_moments")
 
     # ------------------------------------------------------------------ display accumulate
     def display_render(self, cols, stats, rows_max=30, first=0, step=1, n_renders=None, guard_zero_range=False):
@@ -229,24 +237,84 @@ class Context:
                                             n_renders, 1 if guard_zero_range else 0, _ptr(norm), _ptr(minmax)),
                  "pss_display_render_dev")
 
+    # ------------------------------------------------------------------ stateful display streams
+    def display_open(self, stream: int, kind: str = "waterfall", W: int = 200, rows_max: int = 30, H: int = 0):
+        """Create / reset display stream `stream`: the device-resident ring that plays the role of the
+        reference's global WATERFALL_HISTORY / PERSISTENCE_HISTORY lists (pyspecsdr.py:130-131, 151-153)."""
+        self._ck(lib.pss_display_open(self._h, stream, self.QUANT[kind], W, rows_max, H), "pss_display_open")
+        self._streams[stream] = (kind, W, rows_max, H)
+
+    def display_close(self, stream: int):
+        self._ck(lib.pss_display_close(self._h, stream), "pss_display_close")
+        self._streams.pop(stream, None)
+
+    def display_rows(self, stream: int) -> int:
+        return int(lib.pss_display_rows(self._h, stream))
+
+    def display_accumulate(self, stream: int, rows, want=("norm64", "minmax64", "plane_a", "plane_b", "n_rows")):
+        """Feed fp64 dB rows [n_rows, n_bins] (host) to a display stream, one render after every row - the
+        call pattern of draw_waterfall / draw_gradient_waterfall / draw_persistence / draw_surface_plot.
+        fp64 in numpy's operation order: the planes equal what the reference draws from the same rows.
+        Returns dict(norm64 [n, rows_max, W], minmax64 [n, 2], plane_a, plane_b uint8 [n, rows_max, W],
+        n_rows [n]); newest row first, NaN / 255 beyond the history."""
+        kind, W, R, H = self._streams[stream]
+        x = np.ascontiguousarray(rows, dtype=np.float64)
+        if x.ndim == 1:
+            x = x[None, :]
+        n, nb = x.shape
+        shapes = {"norm": ((n, R, W), np.float32), "norm64": ((n, R, W), np.float64), "minmax64": ((n, 2), np.float64),
+                  "plane_a": ((n, R, W), np.uint8), "plane_b": ((n, R, W), np.uint8), "n_rows": ((n,), np.int32)}
+        res = {k: np.empty(*shapes[k]) for k in want}
+        out = DisplayOut(**{k: v.ctypes.data for k, v in res.items()})
+        self._ck(lib.pss_display_accumulate_f64(self._h, stream, x.ctypes.data, nb, n, C.byref(out)),
+                 "pss_display_accumulate_f64")
+        if kind == "surface" and "n_rows" in res:
+            res["n_rows"][:] = 1
+        return res
+
+    def display_accumulate_dev(self, stream: int, cols, stats, n_frames, first=0, step=1, n_renders=None, norm=None,
+                               minmax=None, plane_a=None, plane_b=None, n_rows=None):
+        """Device float32 rows from the PSD kernel (`cols`, `stats`) into a display stream; enqueue only."""
+        if n_renders is None:
+            n_renders = (n_frames - 1 - first) // max(step, 1) + 1
+        out = DisplayOut(norm=_ptr(norm), minmax=_ptr(minmax), plane_a=_ptr(plane_a), plane_b=_ptr(plane_b),
+                         n_rows=_ptr(n_rows))
+        self._ck(lib.pss_display_accumulate_dev(self._h, stream, _ptr(cols), _ptr(stats), n_frames, first, step,
+                                                n_renders, C.byref(out)), "pss_display_accumulate_dev")
+
     # ------------------------------------------------------------------ batched main-loop iteration
     def pipeline(self, blocks, fs: float, mode: str = "WFM", n_fft: int = 4096, W: int = 200, rows_max: int = 30,
-                 want_db: bool = False, out=None):
+                 want_db: bool = False, out=None, display_stream: int = -1, want_planes: bool = False):
         """Host buffers in, host buffers out: demodulate_signal + compute_fft/epilogue on every
         `n_fft` frame + waterfall accumulate after every block, for a batch of blocks.
         `blocks` is complex64 [n_blocks, N_block] (a pinned buffer makes the copies fast).
-        Returns dict(audio, cols, stats, norm, minmax[, db]).  `out` may supply preallocated arrays."""
+        Returns dict(audio, cols, stats, norm, minmax[, db][, plane_a, plane_b]).  `out` may supply
+        preallocated arrays (checked: float32 / uint8, C-contiguous, exact shape).
+        `display_stream` >= 0: a stream from display_open(); its history is carried across calls."""
         x = blocks if (isinstance(blocks, np.ndarray) and blocks.dtype == np.complex64 and blocks.ndim == 2
                        and blocks.flags.c_contiguous) else _as_frames(blocks)
         nb, N = x.shape
         fpb = N // n_fft
         plan = self.demod_plan(mode, fs, N) if mode else None
         o = out if out is not None else {}
-        def buf(name, shape):
+        def buf(name, shape, dtype=np.float32):
             if name not in o:
-                o[name] = np.empty(shape, np.float32)
-            return o[name]
+                o[name] = np.empty(shape, dtype)
+            a = o[name]
+            if not (isinstance(a, np.ndarray) and a.dtype == dtype and a.shape == tuple(shape) and a.flags.c_contiguous):
+                raise ValueError(f"out[{name!r}] must be a C-contiguous {np.dtype(dtype).name} array of shape {tuple(shape)}")
+            return a
+        if display_stream >= 0:
+            if display_stream not in self._streams:
+                raise PssError(f"display stream {display_stream} is not open")
+            _, sw, sr, _ = self._streams[display_stream]
+            if (sw, sr) != (W, rows_max):
+                raise ValueError("display stream geometry differs from W / rows_max")
         io = PipelineIO(N, n_fft, W, rows_max, plan._h if plan else None)
+        io.display_stream = display_stream
+        if want_planes:
+            io.plane_a = buf("plane_a", (nb, rows_max, W), np.uint8).ctypes.data
+            io.plane_b = buf("plane_b", (nb, rows_max, W), np.uint8).ctypes.data
         if plan:
             io.audio = buf("audio", (nb, plan.out_len, plan.channels)).ctypes.data
         io.cols = buf("cols", (nb * fpb, W)).ctypes.data
@@ -321,21 +389,30 @@ class Context:
                  "pss_classify_c64_dev")
 
     def to_int16(self, audio) -> np.ndarray:
-        """write_audio_samples' numeric line (audio_processing.py:36-38): np.int16(samples * 32767)."""
-        a = np.ascontiguousarray(audio, dtype=np.float32)
+        """write_audio_samples' numeric line (audio_processing.py:36-38): np.int16(samples * 32767).
+        float64 input (what the reference holds there) takes the fp64 entry point: bit-identical to numpy."""
+        a = np.asarray(audio)
         out = np.empty(a.shape, np.int16)
-        self._ck(lib.pss_audio_to_int16(self._h, a.ctypes.data, a.size, out.ctypes.data), "pss_audio_to_int16")
+        if a.dtype == np.float32:
+            a = np.ascontiguousarray(a)
+            self._ck(lib.pss_audio_to_int16(self._h, a.ctypes.data, a.size, out.ctypes.data), "pss_audio_to_int16")
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float64)
+            self._ck(lib.pss_audio_to_int16_f64(self._h, a.ctypes.data, a.size, out.ctypes.data),
+                     "pss_audio_to_int16_f64")
         return out
 
     def spectrum_normalise(self, db_rows, W: int):
         """draw_spectrogram's numeric part (pyspecsdr.py:418-452).  Returns (cols [F, W] in [0,1],
         range [F, 2] = display_min, display_max)."""
-        d = np.ascontiguousarray(db_rows, dtype=np.float32)
+        d = np.asarray(db_rows)
+        dt, fn = (np.float64, lib.pss_spectrum_normalise_f64) if d.dtype == np.float64 else (np.float32, lib.pss_spectrum_normalise)
+        d = np.ascontiguousarray(d, dtype=dt)
         fr = d[None, :] if d.ndim == 1 else d
-        cols = np.empty((len(fr), W), np.float32)
-        rng = np.empty((len(fr), 2), np.float32)
-        self._ck(lib.pss_spectrum_normalise(self._h, fr.ctypes.data, fr.shape[1], fr.shape[0], W, cols.ctypes.data,
-                                            rng.ctypes.data), "pss_spectrum_normalise")
+        cols = np.empty((len(fr), W), dt)
+        rng = np.empty((len(fr), 2), dt)
+        self._ck(fn(self._h, fr.ctypes.data, fr.shape[1], fr.shape[0], W, cols.ctypes.data, rng.ctypes.data),
+                 "pss_spectrum_normalise")
         return cols, rng
 
     def surface_row(self, cols, stats):

@@ -88,6 +88,21 @@ void pss_destroy(pss_ctx* ctx) {
     cudaFree(ctx->d_aux);
     cudaFree(ctx->d_aux2);
     for (void* b : ctx->p_buf) cudaFree(b);
+    for (auto& kv : ctx->large_tables) {
+        pss_large_tables& lt = kv.second;
+        cudaFree(lt.tw1); cudaFree(lt.thi); cudaFree(lt.tlo); cudaFree(lt.twN);
+        for (void* w : lt.window) cudaFree(w);
+    }
+    cudaFree(ctx->hann_periodic);
+    pss_pipe_streams& ps = ctx->pipe;
+    if (ps.h2d) cudaStreamDestroy(ps.h2d);
+    if (ps.d2h) cudaStreamDestroy(ps.d2h);
+    for (int i = 0; i < 2; ++i) {
+        if (ps.in_ready[i]) cudaEventDestroy(ps.in_ready[i]);
+        if (ps.in_free[i]) cudaEventDestroy(ps.in_free[i]);
+    }
+    if (ps.done) cudaEventDestroy(ps.done);
+    if (ps.db_free) cudaEventDestroy(ps.db_free);
     cudaStreamDestroy(ctx->own_stream);
     delete ctx;
 }
@@ -131,6 +146,7 @@ void pss_host_free(void* p) {
 int pss_psd_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, int window, int epilogue,
                 int precision, const pss_psd_out* out) {
     if (!ctx || !iq || !out || n_frames < 0 || N <= 0) return PSS_ERR_ARG;
+    if (out->struct_size != sizeof(pss_psd_out)) return PSS_ERR_ARG;
     if (n_frames == 0) return PSS_OK;
     PSS_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n_out = epilogue == PSS_EPI_SMOOTH_CLAMP ? (size_t)N - 4 : (size_t)N;

@@ -12,7 +12,7 @@
 
 #include "../../include/pss.h"
 
-#define PSS_VERSION 100
+#define PSS_VERSION 200
 
 struct pss_fft_tables {
     void* twiddle = nullptr;   // device: per-pass base twiddles, complex<T>
@@ -20,6 +20,24 @@ struct pss_fft_tables {
 };
 
 struct pss_demod_plan;  // pss_demod.cu
+
+// tables of the large transforms (pss_psd.cu), keyed by log2 N
+struct pss_large_tables {
+    void *tw1 = nullptr, *thi = nullptr, *tlo = nullptr;   // big path: W_N1^k, W_N^(1024 j), W_N^j
+    void* twN = nullptr;                                   // cx<double>[N2]: W_N^n2
+    void* window[3] = {nullptr, nullptr, nullptr};
+    bool ready = false;                                    // set only after every allocation succeeded
+};
+
+// copy / compute overlap of pss_pipeline_c64 (pss_pipeline.cu)
+struct pss_pipe_streams {
+    cudaStream_t h2d = nullptr, d2h = nullptr;
+    cudaEvent_t in_ready[2] = {nullptr, nullptr};     // H2D of slot s finished
+    cudaEvent_t in_free[2] = {nullptr, nullptr};      // kernels reading slot s finished
+    cudaEvent_t done = nullptr;                       // kernels of the chunk finished
+    cudaEvent_t db_free = nullptr;                    // D2H of the db scratch finished
+    bool ready = false;
+};
 
 struct pss_ctx {
     int device = 0;
@@ -42,6 +60,10 @@ struct pss_ctx {
     std::map<std::string, pss_demod_plan*> demod_plans;
     // display rings (pss_display.cu)
     std::map<int, void*> displays;
+    // large-transform tables (pss_psd.cu), classifier window, pipeline streams: all owned by the context
+    std::map<int, pss_large_tables> large_tables;
+    void* hann_periodic = nullptr;
+    pss_pipe_streams pipe;
 };
 
 int pss_fail_cuda(pss_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
@@ -58,6 +80,9 @@ int pss_fail_cuda(pss_ctx* ctx, cudaError_t e, const char* what, const char* fil
         if (_e != cudaSuccess) return pss_fail_cuda((ctx), _e, "kernel launch", __FILE__, __LINE__); \
         (ctx)->launches++;                                                           \
     } while (0)
+
+// geometry of an open display stream (pss_display.cu); PSS_ERR_ARG if it does not exist
+int pss_display_geom(const pss_ctx* ctx, int stream, int* W, int* rows_max);
 
 // grow-only device scratch
 int pss_reserve(pss_ctx* ctx, void** p, size_t* have, size_t need);

@@ -23,6 +23,7 @@ struct DecimDev {
     int mode, N, L, q, n_out, lead, SF, SB, n_body, m_tail, tail_start, tail_len;
     int Bf, Bb;
     int Kp, KS, NT, rows, T, nbuf, tile_floats;
+    int iq_correct;                             // WFM: 1 = iq_correction fused in front of the discriminator
     float scale, norm;
     const double *tabF, *AF, *AFB, *AB, *ABB, *MB, *CR, *CB, *head, *tailT, *tailM;
     double DB;
@@ -305,7 +306,7 @@ demod_decim_kernel(const DecimDev D, const float2* __restrict__ iq, float* __res
     for (long long frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
         const float2* x = iq + frame * D.N;
         IqCorr kc = {1.f, 1.f, 0.f, 1.f};
-        if (WFM) {
+        if (WFM && D.iq_correct) {
             // second moments over the block (fp64 accumulation), then iq_correction's estimates
             // (per-thread float partials over N/256 samples, combined in fp64: the same order of
             // rounding error as numpy's own float32 pairwise means at :52, :60, :61)
@@ -570,6 +571,7 @@ static int create_decim(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* p
     D.tail_start = d->tail_start; D.tail_len = d->tail_len;
     D.Bf = d->scan_block_f; D.Bb = d->scan_block_b;
     D.scale = d->scale; D.norm = d->norm; D.DB = d->DB;
+    D.iq_correct = d->iq_correct ? 1 : 0;
     D.rows = D.SF + D.SB + 1;
     D.NT = (D.rows + 7) / 8;
     const int win = D.q + D.lead;
@@ -1171,6 +1173,7 @@ extern "C" {
 
 int pss_demod_plan_create(pss_ctx* ctx, const pss_demod_desc* desc, pss_demod_plan** out) {
     if (!ctx || !desc || !out || desc->N < 2) return PSS_ERR_ARG;
+    if (desc->struct_size != sizeof(pss_demod_desc)) return PSS_ERR_ARG;
     *out = nullptr;
     PSS_CUDA(ctx, cudaSetDevice(ctx->device));
     pss_demod_plan* pl = new (std::nothrow) pss_demod_plan();
@@ -1205,6 +1208,7 @@ void pss_demod_plan_destroy(pss_ctx* ctx, pss_demod_plan* pl) {
 }
 
 int pss_demod_plan_out_len(const pss_demod_plan* pl) { return pl ? pl->out_len : 0; }
+int pss_demod_plan_block_len(const pss_demod_plan* pl) { return pl ? pl->N : 0; }
 int pss_demod_plan_channels(const pss_demod_plan* pl) { return pl ? pl->channels : 0; }
 
 int pss_demod_c64_dev(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t n_frames, float* audio) {
@@ -1215,9 +1219,10 @@ int pss_demod_c64_dev(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t
 }
 
 int pss_demod_c64_dev_moments(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t n_frames, float* audio,
-                              const double* moments, int frames_per_block) {
+                              const double* moments, int frames_per_block, int frame_len) {
     if (!ctx || !pl || !iq || !audio || n_frames < 0) return PSS_ERR_ARG;
-    if (moments && frames_per_block < 1) return PSS_ERR_ARG;
+    // the moment rows must tile the plan's block exactly, or the kernel would sum rows of another block
+    if (moments && (frames_per_block < 1 || (long long)frames_per_block * frame_len != pl->N)) return PSS_ERR_ARG;
     if (n_frames == 0) return PSS_OK;
     if (pl->kind == PSS_PLAN_DECIM && pl->dec.SF == 16) return launch_decim(ctx, pl, iq, n_frames, audio, moments, frames_per_block);
     return pss_demod_c64_dev(ctx, pl, iq, n_frames, audio);
@@ -1244,6 +1249,7 @@ int pss_demod_c64(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t n_f
 int pss_iq_correct_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, float* out) {
     if (!ctx || !iq || !out || N < 2 || n_frames < 0) return PSS_ERR_ARG;
     pss_demod_desc d{};
+    d.struct_size = sizeof d;
     d.kind = PSS_PLAN_RAW;
     d.mode = PSS_MODE_RAW;
     d.N = N;
@@ -1261,6 +1267,7 @@ int pss_sosfilt_f32(pss_ctx* ctx, const float* x, int N, int64_t n_frames, const
     if (!ctx || !x || !y || !sos || N < 1 || n_frames < 0) return PSS_ERR_ARG;
     if (n_frames == 0) return PSS_OK;
     pss_demod_desc d{};
+    d.struct_size = sizeof d;
     d.kind = PSS_PLAN_SOS;
     d.mode = PSS_MODE_AM;
     d.N = N;

@@ -34,6 +34,13 @@ __global__ void int16_kernel(const float* __restrict__ a, const long long n, int
     if (i < n) out[i] = (int16_t)(int)((double)a[i] * 32767.0);     // C cast: truncation toward zero
 }
 
+// np.int16(samples * 32767) on the float64 array the reference holds (audio_processing.py:36-38): one fp64
+// product, then the C cast (truncation toward zero; wrap-around of out-of-range values like the x86 cast).
+__global__ void int16_f64_kernel(const double* __restrict__ a, const long long n, int16_t* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int16_t)(int)__dmul_rn(a[i], 32767.0);
+}
+
 extern "C" {
 
 int pss_power_c64(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, float* power_db) {
@@ -62,6 +69,21 @@ int pss_audio_to_int16(pss_ctx* ctx, const float* audio, int64_t n, int16_t* pcm
     if ((rc = pss_reserve(ctx, &ctx->d_out, &ctx->d_out_bytes, (size_t)n * 2))) return rc;
     PSS_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, audio, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
     int16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const float*)ctx->d_in, n, (int16_t*)ctx->d_out);
+    PSS_LAUNCH_CHECK(ctx);
+    PSS_CUDA(ctx, cudaMemcpyAsync(pcm, ctx->d_out, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    PSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return PSS_OK;
+}
+
+int pss_audio_to_int16_f64(pss_ctx* ctx, const double* audio, int64_t n, int16_t* pcm) {
+    if (!ctx || !audio || !pcm || n < 0) return PSS_ERR_ARG;
+    if (n == 0) return PSS_OK;
+    PSS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_in, &ctx->d_in_bytes, (size_t)n * 8))) return rc;
+    if ((rc = pss_reserve(ctx, &ctx->d_out, &ctx->d_out_bytes, (size_t)n * 2))) return rc;
+    PSS_CUDA(ctx, cudaMemcpyAsync(ctx->d_in, audio, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int16_f64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const double*)ctx->d_in, n, (int16_t*)ctx->d_out);
     PSS_LAUNCH_CHECK(ctx);
     PSS_CUDA(ctx, cudaMemcpyAsync(pcm, ctx->d_out, (size_t)n * 2, cudaMemcpyDeviceToHost, ctx->stream));
     PSS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

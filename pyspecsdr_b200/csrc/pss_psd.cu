@@ -31,7 +31,7 @@ struct PsdParams {
     float* peak;
     int* count;
     int use_abs;
-    float thr;
+    double thr_pow;       // scanner threshold in the power domain: 10^(thr/10) (absolute) or 10^(-rel/10) (x peak)
     const void* ystage;   // second stage of a large transform: cx<T> rows [n_frames][N] (LOG2N1 > 0)
     double* moments;      // [n_frames][4] sum I^2, Q^2, IQ of each frame (by-product for the WFM demod), or null
     int ahead;            // CTAs resident on the device: CTA b prefetches the frames of CTA b + ahead into L2
@@ -260,8 +260,11 @@ psd_kernel(const PsdParams p) {
 
     // ---- |X|^2 -> dB at the fft-shifted position
     auto emit = [&](int k, const cx<T> X) {
-        float d;
-        if constexpr (sizeof(T) == 8) {
+        float d = 0.f;
+        [[maybe_unused]] double pw = 0.0;
+        if constexpr (EPI == EPI_SCAN) {
+            pw = (double)X.x * (double)X.x + ((double)X.y * (double)X.y + 1e-10);
+        } else if constexpr (sizeof(T) == 8) {
             d = db_from_power((double)X.x * (double)X.x + ((double)X.y * (double)X.y + 1e-10));
         } else {            // PSS_PREC_FP32 fast mode: the whole chain in float (does NOT meet 1e-4 dB)
             const float pf = (float)X.x * (float)X.x + ((float)X.y * (float)X.y + 1e-10f);
@@ -277,13 +280,13 @@ psd_kernel(const PsdParams p) {
             if (live) p.db[fb * ntot + (bin ^ (ntot >> 1))] = d;
         } else if constexpr (EPI == EPI_RAW) {
             if (live) p.db[frame * N + pos] = d;
+        } else if constexpr (EPI == EPI_SCAN) {
+            reinterpret_cast<double*>(buf)[pos] = pw;        // fp64 power row (the exchange buffer is dead)
         } else {
             row[pos] = d;
-            if constexpr (EPI == EPI_SMOOTH) {
-                rmin = fminf(rmin, d);
-                rmax = fmaxf(rmax, d);
-                rnan |= d != d;
-            }
+            rmin = fminf(rmin, d);
+            rmax = fmaxf(rmax, d);
+            rnan |= d != d;
         }
     };
     if constexpr (NP == 2) {
@@ -298,23 +301,28 @@ psd_kernel(const PsdParams p) {
     }
 
     if constexpr (EPI == EPI_SCAN) {
-        // scanner: peak and number of bins above (peak - rel) or above an absolute threshold
+        // scanner: peak and number of bins above (peak - rel) or above an absolute threshold.  The integer
+        // count is taken in the fp64 POWER domain (|X|^2 + 1e-10 against p_max * 10^(-rel/10) or 10^(thr/10)):
+        // the comparison then differs from the reference's dB comparison only on ties at the 1e-15 level,
+        // where a float32 dB row would flip bins within ~1e-5 dB of the threshold.
         const int wf = t >> 5, lane = t & 31, nw = TPF / 32;
+        const double* prow = reinterpret_cast<const double*>(buf);
         __syncthreads();
-        float vals[16];
-        float mx = -INFINITY;
+        double vals[16];
+        double mx = 0.0;
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
-            vals[m] = row[t + m * TPF];
-            mx = fmaxf(mx, vals[m]);
-            if (live && p.db) p.db[frame * N + t + m * TPF] = vals[m];
+            vals[m] = prow[t + m * TPF];
+            mx = fmax(mx, vals[m]);                      // fmax drops NaN like the float row maximum did
+            if (live && p.db) p.db[frame * N + t + m * TPF] = db_from_power(vals[m]);
         }
-        mx = warp_max(mx);
-        if (lane == 0) fscr[wf] = mx;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) dscr[wf] = mx;
         __syncthreads();
-        float peak = fscr[0];
-        for (int w = 1; w < nw; ++w) peak = fmaxf(peak, fscr[w]);
-        const float thr = p.use_abs ? p.thr : peak - p.thr;
+        double pmax = dscr[0];
+        for (int w = 1; w < nw; ++w) pmax = fmax(pmax, dscr[w]);
+        const double thr = p.use_abs ? p.thr_pow : pmax * p.thr_pow;
         int cnt = 0;
 #pragma unroll
         for (int m = 0; m < 16; ++m) cnt += vals[m] > thr;
@@ -324,7 +332,7 @@ psd_kernel(const PsdParams p) {
         if (t == 0 && live) {
             unsigned tot = 0;
             for (int w = 0; w < nw; ++w) tot += uscr[w];
-            p.peak[frame] = peak;
+            p.peak[frame] = (float)(10.0 * log10(pmax));
             p.count[frame] = (int)tot;
         }
     }
@@ -1185,13 +1193,8 @@ static int get_tables(pss_ctx* ctx, int log2n, pss_fft_tables** out, bool fp32 =
 }
 
 
-// Large transforms: N = 2^log2n with 14 <= log2n <= 17.
-struct LargeTables {
-    void *tw1 = nullptr, *thi = nullptr, *tlo = nullptr;   // big path: W_N1^k, W_N^(1024 j), W_N^j
-    void* twN = nullptr;           // cx<double>[N2]: W_N^n2
-    void* window[3] = {nullptr, nullptr, nullptr};
-};
-static std::map<int, LargeTables> g_large_tables[16];
+// Large transforms: N = 2^log2n with 14 <= log2n <= 20; their tables (pss_large_tables) live in the context.
+typedef pss_large_tables LargeTables;
 
 template <int LOG2N2, int LOG2N1>
 static int launch_stage_b(pss_ctx* ctx, const PsdParams& p) {
@@ -1229,8 +1232,8 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
     int rc;
     pss_fft_tables* tab2;
     if ((rc = get_tables(ctx, log2n2, &tab2))) return rc;
-    LargeTables& lt = g_large_tables[ctx->device & 15][log2n];
-    if (!lt.twN) {
+    LargeTables& lt = ctx->large_tables[log2n];
+    if (!lt.ready) {
         std::vector<cx<double>> tw(N2);
         std::vector<double> w(N);
         const long double PI = 3.14159265358979323846264338327950288L;
@@ -1238,7 +1241,7 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
             const long double a = -2.0L * PI * (long double)k / (long double)N;
             tw[k] = {(double)cosl(a), (double)sinl(a)};
         }
-        PSS_CUDA(ctx, cudaMalloc(&lt.twN, N2 * sizeof(cx<double>)));
+        if (!lt.twN) PSS_CUDA(ctx, cudaMalloc(&lt.twN, N2 * sizeof(cx<double>)));
         PSS_CUDA(ctx, cudaMemcpy(lt.twN, tw.data(), N2 * sizeof(cx<double>), cudaMemcpyHostToDevice));
         if (big) {
             const long long N1 = 1LL << log2n1;
@@ -1248,7 +1251,7 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
                     const long double a = -2.0L * PI * num * (long double)k / den;
                     t[k] = {(double)cosl(a), (double)sinl(a)};
                 }
-                PSS_CUDA(ctx, cudaMalloc(dst, count * sizeof(cx<double>)));
+                if (!*dst) PSS_CUDA(ctx, cudaMalloc(dst, count * sizeof(cx<double>)));
                 PSS_CUDA(ctx, cudaMemcpy(*dst, t.data(), count * sizeof(cx<double>), cudaMemcpyHostToDevice));
                 return PSS_OK;
             };
@@ -1259,9 +1262,10 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
         for (int kind = PSS_WINDOW_HAMMING; kind <= PSS_WINDOW_HANN; ++kind) {
             const long double a = kind == PSS_WINDOW_HAMMING ? 0.54L : 0.5L, b = kind == PSS_WINDOW_HAMMING ? 0.46L : 0.5L;
             for (long long i = 0; i < N; ++i) w[i] = (double)(a - b * cosl(2.0L * PI * (long double)i / (long double)(N - 1)));
-            PSS_CUDA(ctx, cudaMalloc(&lt.window[kind], N * sizeof(double)));
+            if (!lt.window[kind]) PSS_CUDA(ctx, cudaMalloc(&lt.window[kind], N * sizeof(double)));
             PSS_CUDA(ctx, cudaMemcpy(lt.window[kind], w.data(), N * sizeof(double), cudaMemcpyHostToDevice));
         }
+        lt.ready = true;           // only now: a failed allocation above leaves the tables to be rebuilt
     }
     if (log2n <= 16 && !big) {
         // fused persistent kernel: per-CTA scratch only (grid * N * 16 bytes of fp64 rows + the raw dB row)
@@ -1376,6 +1380,7 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
 extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_frames, int window,
                                int epilogue, int precision, const pss_psd_out* out) {
     if (!ctx || !iq || !out || n_frames < 0) return PSS_ERR_ARG;
+    if (out->struct_size != sizeof(pss_psd_out)) return PSS_ERR_ARG;
     if (window < 0 || window > 2 || (epilogue != PSS_EPI_RAW && epilogue != PSS_EPI_SMOOTH_CLAMP))
         return PSS_ERR_ARG;
     if (precision != PSS_PREC_FP64 && precision != PSS_PREC_FP32) return PSS_ERR_ARG;
@@ -1428,7 +1433,7 @@ extern "C" int pss_scan_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_
     p.peak = peak_db;
     p.count = count_above;
     p.use_abs = use_abs;
-    p.thr = thr_db;
+    p.thr_pow = use_abs ? pow(10.0, (double)thr_db / 10.0) : pow(10.0, -(double)thr_db / 10.0);
     return launch_by_n<double, EPI_SCAN>(ctx, log2n, p);
 }
 
@@ -1622,8 +1627,6 @@ classify_kernel(const float2* __restrict__ iq, const int N_block, const long lon
     }
 }
 
-static void* g_hann_periodic[16] = {};
-
 extern "C" int pss_classify_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_blocks, double fs,
                                     double* features, int32_t* label) {
     if (!ctx || !iq || !features || !label || n_blocks < 0 || !(fs > 0)) return PSS_ERR_ARG;
@@ -1632,7 +1635,7 @@ extern "C" int pss_classify_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_
     int rc;
     pss_fft_tables* tab;
     if ((rc = get_tables(ctx, 10, &tab))) return rc;
-    void*& hann = g_hann_periodic[ctx->device & 15];
+    void*& hann = ctx->hann_periodic;
     if (!hann) {
         std::vector<double> w(1024);
         for (int i = 0; i < 1024; ++i)      // scipy get_window('hann', 1024): periodic (fftbins=True)

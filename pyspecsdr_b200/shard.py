@@ -67,6 +67,12 @@ def sweep(ctx, frames_dev, N: int, n_steps: int, rank: int, world: int, want_row
     count = torch.empty(n_local, device=dev, dtype=torch.int32)
     rows = torch.empty(n_local, N, device=dev, dtype=torch.float32) if want_rows else None
     if n_local:
+        # Stream contract of the *_dev calls (include/pss.h): the scan runs on the CONTEXT's stream, which has
+        # no ordering with torch's unless the caller adopted it with ctx.set_stream().  So: finish whatever
+        # produced `frames_dev` on torch's current stream, enqueue the scan, and drain the context's stream
+        # before the collective (which runs on torch's / NCCL's streams) may read peak / count / rows.
+        if dev.type == "cuda":
+            torch.cuda.current_stream(dev).synchronize()
         ctx.scan_dev(frames_dev, N, n_local, peak, count, rows=rows, rel_db=rel_db)
-    torch.cuda.current_stream(dev).synchronize() if dev.type == "cuda" else None
+        ctx.sync()
     return gather_sweep(peak, count, rows, n_steps, group)

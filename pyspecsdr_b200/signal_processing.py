@@ -66,10 +66,11 @@ def demodulate_nfm(samples, sample_rate, target_rate=DEFAULT_SAMPLE_RATE):
 
 
 def demodulate_wfm(samples, sample_rate, target_rate=DEFAULT_SAMPLE_RATE):
-    """signal_processing.py:119-176 (expects iq-corrected input like the reference's dispatcher gives
-    it; here the correction is fused into the kernel, see demodulate_signal)."""
+    """signal_processing.py:119-176: the WFM chain on the samples as given, NO iq_correction - exactly
+    like the reference's function (its dispatcher corrects first, :222-225; that fused path is
+    demodulate_signal(..., 'WFM'))."""
     _check_rate(target_rate)
-    return _ctx().demod(_c64(samples), float(sample_rate), "WFM")[0].astype(np.float64)
+    return _ctx().demod(_c64(samples), float(sample_rate), "WFM", iq_correct=False)[0].astype(np.float64)
 
 
 def demodulate_am(samples):

@@ -53,29 +53,57 @@ def test_c4_scanner_sweep_8192_sharded_stitch(ctx):
     assert np.max(np.abs(rows.cpu().numpy() - want)) <= 1e-4
     for k in range(n_steps):
         pk, cnt, _ = O.scan_step(frames[k], 2.4e6)
-        assert abs(float(peak[k]) - pk) <= 1e-4 and abs(int(count[k]) - cnt) <= 1
+        assert abs(float(peak[k]) - pk) <= 1e-4 and int(count[k]) == cnt
 
 
 def test_c5_persistence_surface_16384(ctx):
-    """C5: 16384-pt frames, 10-row persistence history + surface row, W = 200."""
-    n, W, H = 16384, 200, 36
+    """C5: 16384-pt frames, 10-row persistence history + surface row, W = 200, on a carried display
+    stream fed straight from the PSD kernel's device rows (one stream per IQ stream and view).
+    The planes come from float32 spectra (1e-4 dB tolerance), so a cell may differ from the oracle's only
+    where the oracle's own value sits on a quantisation boundary; everything else must be equal."""
+    import torch
+    import _display_cells as D
+    n, W, H, R = 16384, 200, 36, 10
     x = np.stack([synth.make("wbfm" if s % 2 else "tone40", n, seed=200 + s) for s in range(13)])
-    res = ctx.psd(x, epilogue=True, W=W, want_stats=True, want_db=False)
     rows = [O.psd_epilogue(O.psd_db(r)) for r in x]
-    norm, mm = ctx.display_render(res["cols"], res["stats"], rows_max=10, guard_zero_range=True)
-    hist = []
+    dev = torch.device("cuda", 0)
+    xd = torch.from_numpy(x.view(np.float32).reshape(13, n, 2)).to(dev)
+    cols = torch.empty(13, W, device=dev)
+    stats = torch.empty(13, 4, device=dev)
+    ys = torch.empty(13, R, W, device=dev, dtype=torch.uint8)
+    cp = torch.empty(13, R, W, device=dev, dtype=torch.uint8)
+    mm = torch.empty(13, 2, device=dev)
+    mag = torch.empty(13, 1, W, device=dev, dtype=torch.uint8)
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        ctx.display_open(20, "persistence", W=W, rows_max=R, H=H)
+        ctx.display_open(21, "surface", W=W, rows_max=1)
+        for a, b in ((0, 1), (1, 2), (2, 9), (9, 13)):         # the ring is carried from call to call
+            ctx.psd_dev(xd[a:b], n, b - a, epilogue=True, cols=cols[a:b], W=W, stats=stats[a:b])
+            ctx.display_accumulate_dev(20, cols[a:b], stats[a:b], b - a, plane_a=ys[a:b], plane_b=cp[a:b], minmax=mm[a:b])
+            ctx.display_accumulate_dev(21, cols[a:b], stats[a:b], b - a, plane_a=mag[a:b])
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_stream(None)
+        ctx.display_close(20)
+        ctx.display_close(21)
+    ys, cp, mm, mag = ys.cpu().numpy(), cp.cpu().numpy(), mm.cpu().numpy(), mag.cpu().numpy()
+    hist, boundary = [], 0
+    tol = 2e-4 / 40.0                       # 2 x the dB tolerance over a >= 40 dB stack range, in normalised units
     for s, r in enumerate(rows):
-        ys, colours, (lo, hi) = O.persistence_accumulate(hist, r, W, H)
-        got = norm[s, :len(hist)][::-1]
-        y = ((1 - got.astype(np.float64)) * (H - 1)).astype(np.int64)
-        assert np.max(np.abs(y - ys)) <= 1 and np.mean(y != ys) <= 2e-3
-        assert abs(mm[s, 0] - lo) <= 1e-4 and abs(mm[s, 1] - hi) <= 1e-4
-    # surface row = the frame normalised by its own range (history of one row), magnitude = int(v * 20)
-    snorm, _ = ctx.display_render(res["cols"], res["stats"], rows_max=1, guard_zero_range=True)
-    for s in (0, 7, 12):
-        mag, _ = O.surface_row(rows[s], W)
-        got = (snorm[s, 0].astype(np.float64) * 20).astype(np.int64)
-        assert np.max(np.abs(got - mag)) <= 1 and np.mean(got != mag) <= 0.02
+        ref_y, colours, (lo, hi) = O.persistence_accumulate(hist, r, W, H)
+        L = len(hist)
+        assert hi - lo >= 40.0 and abs(mm[s, 0] - lo) <= 1e-4 and abs(mm[s, 1] - hi) <= 1e-4
+        ref_norm = np.stack([(O.resample_cols(line, W) - lo) / (hi - lo) for line in hist])
+        got = ys[s, :L][::-1]
+        boundary += D.assert_equal_or_on_boundary(got, 1 - ref_norm, H - 1, tol, f"persistence y, frame {s}")
+        np.testing.assert_array_equal(cp[s, :L, 0][::-1], colours)
+        assert np.all(ys[s, L:] == 255)
+        fin = r[np.isfinite(r)]
+        rl, rh = fin.min(), fin.max()
+        ref_surf = O.resample_cols((r - rl) / (rh - rl), W)
+        boundary += D.assert_equal_or_on_boundary(mag[s, 0], ref_surf, 20, tol, f"surface, frame {s}")
+    assert boundary <= 13 * (R + 1) * W * 1e-3
 
 
 def test_capture_file_processing_sharded(ctx, tmp_path):

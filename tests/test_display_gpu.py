@@ -1,8 +1,15 @@
-"""GPU parity: display accumulate (waterfall / gradient / persistence history normalisation) vs the
-oracle, which is itself pinned through what the reference's draw_* functions drew."""
+"""GPU parity: display accumulate fed by the PSD kernel's float32 rows (IQ in -> display values out) vs the
+oracle, which is itself pinned through what the reference's draw_* functions drew.
+
+Floating-point outputs: within the stated tolerance.  Integer planes on this path are derived from spectra
+that carry the 1e-4 dB tolerance, so they must EQUAL the oracle's except in cells where the oracle's own
+value lies on a quantisation boundary (`assert_equal_or_on_boundary`; the count of such cells is bounded).
+The planes themselves are bit-exact given the same dB rows: tests/test_exact_gpu.py checks that against the
+cells the reference drew."""
 import numpy as np
 import pytest
 
+import _display_cells as D
 from oracle import ref_dsp as O
 from pyspecsdr_b200 import synth
 
@@ -21,17 +28,12 @@ def test_waterfall_history_vs_oracle(ctx):
     res = ctx.psd(x, epilogue=True, W=W, want_stats=True, want_db=False)
     norm, mm = ctx.display_render(res["cols"], res["stats"], rows_max=30)
     hist = []
-    mism = 0
     for s, r in enumerate(ref_rows):
         want, (lo, hi), colour, level = O.waterfall_accumulate(hist, r, W)
         got = norm[s, :len(hist)]
         assert abs(mm[s, 0] - lo) <= 1e-4 and abs(mm[s, 1] - hi) <= 1e-4
         assert np.max(np.abs(got - want)) <= 1e-5
         assert np.all(np.isnan(norm[s, len(hist):]))
-        # quantised planes (colour index, glyph level) agree except where norm sits on a boundary
-        mism += np.sum((got * 5).astype(np.int64) != colour)
-        mism += np.sum(((got > 0.25).astype(int) + (got > 0.5) + (got > 0.75)) != level)
-    assert mism <= 1e-4 * 2 * 34 * 30 * W
 
 
 def test_persistence_history_vs_oracle(ctx):
@@ -40,14 +42,11 @@ def test_persistence_history_vs_oracle(ctx):
     res = ctx.psd(x, epilogue=True, W=W, want_stats=True, want_db=False)
     norm, mm = ctx.display_render(res["cols"], res["stats"], rows_max=10, guard_zero_range=True)
     hist = []
-    bad = 0
     for s, r in enumerate(ref_rows):
         ys, colours, (lo, hi) = O.persistence_accumulate(hist, r, W, H)
         got = norm[s, :len(hist)][::-1]                      # oldest first, like PERSISTENCE_HISTORY
-        y = ((1 - got.astype(np.float64)) * (H - 1)).astype(np.int64)
-        bad += np.sum(y != ys)
-        assert np.max(np.abs(y - ys)) <= 1
-    assert bad <= 1e-3 * 14 * 10 * W
+        want = np.stack([(O.resample_cols(line, W) - lo) / (hi - lo) for line in hist])
+        assert np.max(np.abs(got - want)) <= 1e-5
 
 
 def test_display_strided_renders(ctx):
@@ -97,39 +96,71 @@ def test_spectrum_normalise_vs_oracle(ctx):
         assert np.max(np.abs(cols[f] - want)) <= 2e-5
 
 
-def test_surface_row_vs_oracle(ctx):
-    x, ref_rows = make_rows(5, 4096)
-    W = 112
-    res = ctx.psd(x, epilogue=True, W=W, want_stats=True, want_db=False)
-    mag, _ = ctx.surface_row(res["cols"], res["stats"])
-    for f, r in enumerate(ref_rows):
-        want, _ = O.surface_row(r, W)
-        assert np.max(np.abs(mag[f] - want)) <= 1 and np.mean(mag[f] != want) <= 0.02
+TOL_NORM = 2e-4 / 40.0      # 2 x the dB tolerance over a >= 40 dB display range, in normalised units
 
 
-def test_display_quantised_planes_vs_oracle(ctx):
-    """8f-3: glyph / colour planes (what the reference computes per cell in Python loops)."""
+def test_planes_from_iq_equal_oracle_except_on_boundaries(ctx):
+    """8f-3 on the product path: IQ -> PSD kernel (float32 rows on the device) -> carried display streams
+    -> uint8 planes (what the reference computes per cell in Python loops)."""
+    import torch
     x, ref_rows = make_rows(32, 4096)
     W, H = 112, 36
-    res = ctx.psd(x, epilogue=True, W=W, want_stats=True, want_db=False)
-    norm, _ = ctx.display_render(res["cols"], res["stats"], rows_max=30)
-    level, colour = ctx.display_quantise(norm[-1], "waterfall")
-    hist = []
-    for r in ref_rows:
-        want_norm, _, want_colour, want_level = O.waterfall_accumulate(hist, r, W)
-    assert np.mean(level != want_level) <= 1e-3 and np.mean(colour != want_colour) <= 1e-3
-    gnorm, _ = ctx.display_render(res["cols"], res["stats"], rows_max=30, guard_zero_range=True)
-    chars, colour = ctx.display_quantise(gnorm[-1], "gradient")
-    hist = []
-    for r in ref_rows:
-        _, _, want_chars, want_colour = O.gradient_accumulate(hist, r, W)
-    assert np.mean(chars != want_chars) <= 1e-3 and np.mean(colour != want_colour) <= 1e-3
-    # rows older than the history are marked 255
-    early, _ = ctx.display_quantise(norm[2], "waterfall")
-    assert np.all(early[3:] == 255) and np.all(early[:3] < 4)
-    pn, _ = ctx.display_render(res["cols"][:10], res["stats"][:10], rows_max=10, guard_zero_range=True)
-    ys, _ = ctx.display_quantise(pn[-1][::-1], "persistence", H=H)
-    hist = []
-    for r in ref_rows[:10]:
-        want_ys, _, _ = O.persistence_accumulate(hist, r, W, H)
-    assert np.mean(ys != want_ys) <= 2e-3 and np.max(np.abs(ys.astype(int) - want_ys)) <= 1
+    dev = torch.device("cuda", 0)
+    xd = torch.from_numpy(x.view(np.float32).reshape(32, 4096, 2)).to(dev)
+    cols = torch.empty(32, W, device=dev)
+    stats = torch.empty(32, 4, device=dev)
+    planes = {k: (torch.empty(32, r, W, device=dev, dtype=torch.uint8), torch.empty(32, r, W, device=dev, dtype=torch.uint8))
+              for k, r in (("waterfall", 30), ("gradient", 30), ("persistence", 10), ("surface", 1))}
+    ctx.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+    try:
+        ctx.psd_dev(xd, 4096, 32, epilogue=True, cols=cols, W=W, stats=stats)
+        for i, (k, (pa, pb)) in enumerate(planes.items()):
+            ctx.display_open(30 + i, k, W=W, rows_max=pa.shape[1], H=H if k == "persistence" else 0)
+            ctx.display_accumulate_dev(30 + i, cols, stats, 32, plane_a=pa, plane_b=pb)
+            ctx.display_close(30 + i)
+        torch.cuda.synchronize()
+    finally:
+        ctx.set_stream(None)
+    P = {k: (a.cpu().numpy(), b.cpu().numpy()) for k, (a, b) in planes.items()}
+    hw, hp, nb = [], [], 0
+    for s, r in enumerate(ref_rows):
+        want_norm, (lo, hi), _, want_level = O.waterfall_accumulate(hw, r, W)
+        L = len(hw)
+        assert hi - lo >= 40.0
+        nb += D.assert_equal_or_on_boundary(P["waterfall"][1][s, :L], want_norm, 5, TOL_NORM, "waterfall colour")
+        bad = P["waterfall"][0][s, :L] != want_level                      # '.', '-', '=', '#': strict > 0.25, 0.5, 0.75
+        if bad.any():
+            assert np.all(np.min(np.abs(want_norm[bad][:, None] - np.array([0.25, 0.5, 0.75])), axis=1) <= TOL_NORM)
+            nb += int(bad.sum())
+        nb += D.assert_equal_or_on_boundary(P["gradient"][0][s, :L], want_norm, 8, TOL_NORM, "gradient glyph")
+        nb += D.assert_equal_or_on_boundary(P["gradient"][1][s, :L], want_norm, 5, TOL_NORM, "gradient colour")
+        assert np.all(P["waterfall"][0][s, L:] == 255)
+        ys, colours, (plo, phi) = O.persistence_accumulate(hp, r, W, H)
+        Lp = len(hp)
+        pn = np.stack([(O.resample_cols(line, W) - plo) / (phi - plo) for line in hp])
+        nb += D.assert_equal_or_on_boundary(P["persistence"][0][s, :Lp][::-1], 1 - pn, H - 1, TOL_NORM, "persistence y")
+        np.testing.assert_array_equal(P["persistence"][1][s, :Lp, 0][::-1], colours)
+        fin = r[np.isfinite(r)]
+        surf = O.resample_cols((r - fin.min()) / (fin.max() - fin.min()), W)
+        nb += D.assert_equal_or_on_boundary(P["surface"][0][s, 0], surf, 20, TOL_NORM, "surface magnitude")
+    assert nb <= 2e-4 * 32 * 72 * W          # a handful of boundary cells out of ~258 000
+
+
+def test_quantise_call_matches_stream_planes(ctx):
+    """pss_display_quantise (planes from already-normalised float32 values) uses the same rules."""
+    v = np.linspace(-0.1, 1.1, 1201).astype(np.float32)
+    v[7] = np.nan
+    d = v.astype(np.float64)
+    a, b = ctx.display_quantise(v, "waterfall")
+    ok = np.isfinite(d)
+    np.testing.assert_array_equal(a[ok], ((d > 0.25).astype(int) + (d > 0.5) + (d > 0.75))[ok])
+    np.testing.assert_array_equal(b[ok], np.clip((d * 5).astype(np.int64), 0, 254)[ok])
+    assert a[7] == 255 and b[7] == 255
+    a, _ = ctx.display_quantise(v, "gradient")
+    np.testing.assert_array_equal(a[ok], np.clip((d * 8).astype(np.int64), 0, 254)[ok])
+    a, _ = ctx.display_quantise(v, "surface")
+    np.testing.assert_array_equal(a[ok], np.clip((d * 20).astype(np.int64), 0, 254)[ok])
+    a, _ = ctx.display_quantise(v, "persistence", H=36)
+    y = ((1 - d) * 35).astype(np.int64)
+    want = np.where((y >= 0) & (y < 36), y, 255)
+    np.testing.assert_array_equal(a[ok], want[ok])

@@ -184,3 +184,75 @@ def test_tools_and_bench_compile():
     assert len(files) >= 8
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+# ------------------------------------------------------------------ import-level drop-in
+_APP_PROBE = r"""
+import sys, types, json
+root, ref = sys.argv[1], sys.argv[2]
+sys.path[:0] = [root + "/shim", root, ref]
+soapy = types.ModuleType("SoapySDR"); soapy.SOAPY_SDR_RX = 0; soapy.SOAPY_SDR_CF32 = "CF32"
+sd = types.ModuleType("sounddevice"); sd.PortAudioError = Exception
+sys.modules["SoapySDR"] = soapy; sys.modules["sounddevice"] = sd
+import warnings
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    import pyspecsdr as app          # the UNMODIFIED application module
+    import decoders
+names = ["compute_fft", "demodulate_signal", "measure_signal_power", "classify_signal", "bandpass_filter",
+         "iq_correction", "mono_to_stereo", "demodulate_nfm", "demodulate_wfm", "demodulate_am", "demodulate_ssb",
+         "init_audio_device", "start_audio_recording", "write_audio_samples", "stop_audio_recording"]
+out = {n: getattr(app, n).__module__ for n in names}
+out["decoders.bandpass_filter"] = decoders.bandpass_filter.__module__
+out["has"] = [n for n in ("np", "sd", "wave", "butter", "lfilter", "firwin", "hilbert", "decimate", "bilinear",
+                          "resample_poly", "DEFAULT_SAMPLE_RATE", "BUTTER_ORDER") if hasattr(app, n)]
+out["file"] = app.__file__
+print(json.dumps(out))
+"""
+
+
+def test_unmodified_app_binds_the_gpu_module_through_the_shim():
+    """pyspecsdr.py:98-99 (`from signal_processing import *`, `from audio_processing import *`) and
+    decoders.py:3, imported UNMODIFIED from the reference tree with shim/ ahead on sys.path, bind the
+    functions of pyspecsdr_b200 (SoapySDR / sounddevice are stubbed: neither is installed here)."""
+    ref = "/root/reference"
+    if not os.path.exists(os.path.join(ref, "pyspecsdr.py")):
+        pytest.skip("the reference tree only exists in the build container")
+    import json
+    r = subprocess.run([sys.executable, "-c", _APP_PROBE, ROOT, ref], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out["file"].startswith(ref)
+    for n in ("compute_fft", "demodulate_signal", "measure_signal_power", "classify_signal", "bandpass_filter",
+              "iq_correction", "mono_to_stereo", "demodulate_nfm", "demodulate_wfm", "demodulate_am", "demodulate_ssb"):
+        assert out[n] == "pyspecsdr_b200.signal_processing", (n, out[n])
+    for n in ("init_audio_device", "start_audio_recording", "write_audio_samples", "stop_audio_recording"):
+        assert out[n] == "pyspecsdr_b200.audio_processing", (n, out[n])
+    assert out["decoders.bandpass_filter"] == "pyspecsdr_b200.signal_processing"
+    assert set(out["has"]) >= {"np", "sd", "wave", "butter", "lfilter", "firwin", "hilbert", "decimate", "bilinear",
+                               "resample_poly", "DEFAULT_SAMPLE_RATE", "BUTTER_ORDER"}
+
+
+def test_abi_structs_carry_their_size():
+    """Every struct that crosses the ABI starts with size_t struct_size, in the header and in the ctypes
+    mirror, and the two agree on the layout (field names in order)."""
+    import ctypes as C
+    from pyspecsdr_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "pss.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    mirrors = {"pss_psd_out": _lib.PsdOut, "pss_demod_desc": _lib.DemodDesc, "pss_pipeline_io": _lib.PipelineIO,
+               "pss_display_out": _lib.DisplayOut}
+    structs = re.findall(r"typedef struct \{(.*?)\}\s*(pss_[a-z_]+);", hdr, flags=re.S)
+    assert {n for _, n in structs} == set(mirrors)
+    for body, name in structs:
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(","):
+                fields.append(re.findall(r"([A-Za-z_0-9]+)\s*$", part.replace("*", " ").strip())[0])
+        assert fields[0] == "struct_size", name
+        assert fields == [f[0] for f in mirrors[name]._fields_], name
+        inst = mirrors[name]()
+        assert inst.struct_size == C.sizeof(mirrors[name])

@@ -5,6 +5,7 @@ import hashlib
 import numpy as np
 import pytest
 
+import _display_cells as D
 from oracle import ref_dsp as O
 from pyspecsdr_b200 import synth
 
@@ -123,24 +124,19 @@ def test_int16(golden):
 # what the reference's draw_* functions actually drew on a recording fake screen
 def _rows(golden):
     g = golden("display")
-    rows = []
-    for s in range(34):
-        x = synth.make("wbfm" if s % 2 else "tone40", 4096, seed=100 + s)
-        rows.append(O.psd_epilogue(O.psd_db(x)))
-    assert digest(np.array(rows)) == str(g["rows_in"])
-    return g, rows
+    return g, D.golden_rows(g)
 
 
 def test_waterfall_display(golden):
     g, rows = _rows(golden)
     W = int(g["W"]) - 8
     hist = []
-    glyph = np.array([ord(c) for c in ".-=#"])
     for s, r in enumerate(rows):
         norm, (lo, hi), colour, level = O.waterfall_accumulate(hist, r, W)
         if s in (0, 5, 33):
-            np.testing.assert_array_equal(glyph[level], g[f"waterfall_{s}_char"])
-            np.testing.assert_array_equal((10 + colour) << 8, g[f"waterfall_{s}_attr"])
+            ch, at = D.waterfall_cells(level, colour)
+            np.testing.assert_array_equal(ch, g[f"waterfall_{s}_char"])
+            np.testing.assert_array_equal(at, g[f"waterfall_{s}_attr"])
     assert len(hist) == 30
 
 
@@ -148,12 +144,12 @@ def test_gradient_display(golden):
     g, rows = _rows(golden)
     W = int(g["W"]) - 10
     hist = []
-    glyph = np.array([ord(c) for c in " ._-=+*#@"])
     for s, r in enumerate(rows):
         norm, _, chars, colour = O.gradient_accumulate(hist, r, W)
         if s in (0, 33):
-            np.testing.assert_array_equal(glyph[chars], g[f"gradient_{s}_char"])
-            np.testing.assert_array_equal((10 + colour) << 8, g[f"gradient_{s}_attr"])
+            ch, at = D.gradient_cells(chars, colour)
+            np.testing.assert_array_equal(ch, g[f"gradient_{s}_char"])
+            np.testing.assert_array_equal(at, g[f"gradient_{s}_attr"])
 
 
 def test_persistence_display(golden):
@@ -163,27 +159,16 @@ def test_persistence_display(golden):
     for s, r in enumerate(rows[:14]):
         ys, colours, _ = O.persistence_accumulate(hist, r, W, H)
         if s in (0, 13):
-            want = g[f"persistence_{s}_stars"]
-            got = [(y + 2, x + 8, int(c) << 8) for yrow, c in zip(ys, colours)
-                   for x, y in enumerate(yrow) if 0 <= y < H]
-            np.testing.assert_array_equal(np.array(got, dtype=np.int64), want)
+            np.testing.assert_array_equal(D.persistence_stars(ys, colours, H), g[f"persistence_{s}_stars"])
 
 
 def test_surface_display(golden):
     g, rows = _rows(golden)
     H, Wt = int(g["H"]), int(g["W"])
     mag, _ = O.surface_row(rows[3], Wt - 8)
-    ang = np.radians(O.SURFACE_ANGLE)
-    cells = set()
-    for x, m in enumerate(mag):                       # projection loop, pyspecsdr.py:1594-1601
-        for y in range(int(m)):
-            sx = int(x - y * np.cos(ang)) + 8
-            sy = int(H - 2 - y * np.sin(ang))
-            if 0 <= sx < Wt and 2 <= sy < H - 1:
-                cells.add((sy, sx, (1 + (y % 5)) << 8))
     # the reference overdraws cells; compare the set of (y, x) it touched with '#'
     want = {(int(a), int(b)) for a, b, _ in g["surface_hash_cells"]}
-    assert {(a, b) for a, b, _ in cells} == want
+    assert D.surface_cells(mag, H, Wt) == want
 
 
 def test_spectrum_display(golden):
@@ -192,26 +177,8 @@ def test_spectrum_display(golden):
     dh, dw = H - 4, Wt - 7
     cols, _ = O.spectrum_normalise(rows[3], dw)
     want = {(int(y), int(x)): (int(c), int(a)) for y, x, c, a in g["spectrum_cells"]}
-    import curses
-    for x, v in enumerate(cols):                      # bar logic, pyspecsdr.py:455-493
-        height = min(int(v * dh), dh)
-        for y in range(dh):
-            cell = want[(y + 2, x + 7)]
-            if y < dh - height:
-                assert cell == (ord(" "), 1 << 8)
-                continue
-            rel = (y - (dh - height)) / height if height > 0 else 0
-            if v > 0.8:
-                ch, col = ("#" if rel > 0.5 else "="), 14
-            elif v > 0.4:
-                ch, col = ("=" if rel > 0.5 else "-"), 13
-            elif v > 0.2:
-                ch, col = ("-" if rel > 0.5 else "."), 12
-            elif rel > 0.7:
-                ch, col = ".", 11
-            else:
-                ch, col = " ", 10
-            assert cell == (ord(ch), (col << 8) | curses.A_BOLD), (x, y, v)
+    got = D.spectrum_cells(cols, dh)
+    assert all(want[k] == v for k, v in got.items()) and len(got) == dh * dw
 
 
 def test_classifier_oracle_matches_reference_golden(golden):
