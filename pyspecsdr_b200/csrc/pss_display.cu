@@ -127,8 +127,11 @@ __global__ void __launch_bounds__(256) display_render_kernel(const RenderArgs<T>
         double v = __longlong_as_double(0x7ff8000000000000LL);
         if (y < len) {
             const long long f = t - y;
-            const double col = f >= 0 ? (double)A.cur_cols[f * W + c] : (double)A.prev_cols[((R - 1) + f) * W + c];
-            v = finite_d(col) ? __ddiv_rn(__dsub_rn(col, lo), range) : __longlong_as_double(0x7ff8000000000000LL);
+            const T colT = f >= 0 ? A.cur_cols[f * W + c] : A.prev_cols[((R - 1) + f) * W + c];
+            const double col = (double)colT;
+            if (!finite_d(col)) v = __longlong_as_double(0x7ff8000000000000LL);
+            else if constexpr (sizeof(T) == 8) v = __ddiv_rn(__dsub_rn(col, lo), range);      // numpy's fp64 arithmetic
+            else v = (double)__fdiv_rn(__fsub_rn(colT, (float)lo), (float)range);              // float32 rows: float32 value
         }
         if (A.norm) A.norm[base + e] = (float)v;
         if (A.norm64) A.norm64[base + e] = v;

@@ -150,9 +150,9 @@ def test_quantise_call_matches_stream_planes(ctx):
     """pss_display_quantise (planes from already-normalised float32 values) uses the same rules."""
     v = np.linspace(-0.1, 1.1, 1201).astype(np.float32)
     v[7] = np.nan
-    d = v.astype(np.float64)
+    d = np.nan_to_num(v.astype(np.float64))
     a, b = ctx.display_quantise(v, "waterfall")
-    ok = np.isfinite(d)
+    ok = np.isfinite(v)
     np.testing.assert_array_equal(a[ok], ((d > 0.25).astype(int) + (d > 0.5) + (d > 0.75))[ok])
     np.testing.assert_array_equal(b[ok], np.clip((d * 5).astype(np.int64), 0, 254)[ok])
     assert a[7] == 255 and b[7] == 255

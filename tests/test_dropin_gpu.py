@@ -98,13 +98,13 @@ def test_demodulate_wfm_direct_call_does_not_correct(sp):
     dispatcher applies iq_correction (:222-225).  Direct call == oracle's demod_wfm without correction;
     dispatcher == correction + demod_wfm; and the two differ on an IQ-imbalanced input."""
     x = synth.make("wbfm", 32768, seed=4)
-    x = (x.real * 1.2 + 1j * (x.imag * 0.8 + 0.1 * x.real)).astype(np.complex64)
+    x = (x.real * 1.2 + 1j * (x.imag * 0.5 + 0.3 * x.real)).astype(np.complex64)
     direct = sp.demodulate_wfm(x, 2.4e6)
     ref_direct = O.demod_wfm(x, 2.4e6)
     assert np.sqrt(np.mean((direct - ref_direct) ** 2)) <= 1e-5
     disp = sp.demodulate_signal(x, 2.4e6, "WFM")
     assert np.sqrt(np.mean((disp - O.demod(x, 2.4e6, "WFM")) ** 2)) <= 1e-5
-    assert np.sqrt(np.mean((disp - direct) ** 2)) > 1e-3
+    assert np.sqrt(np.mean((disp - direct) ** 2)) > 5e-4          # the oracle's two forms differ by 1.35e-3 here
     # corrected input through the direct call == the dispatcher, like the reference's two-step form
     two_step = sp.demodulate_wfm(sp.iq_correction(x), 2.4e6)
     assert np.sqrt(np.mean((two_step - disp) ** 2)) <= 1e-5
