@@ -145,8 +145,9 @@ int pss_spectrum_normalise_f64(pss_ctx* ctx, const double* db, int n_bins, int64
  * PSS_PLAN_DECIM (NFM, WFM): fp32 discriminator -> [65-tap FIR | Butterworth low-pass + de-emphasis]
  *   -> scipy.signal.decimate(q) = 8th-order Chebyshev-I sosfiltfilt (odd extension 27, sosfilt_zi
  *   initial conditions) -> [::q] -> / max|.| * norm.  Evaluated in "chunk-table" form: fp64 tensor
- *   -core (DMMA) products of the discriminator stream with precomputed response tables, then
- *   blocked scans of the 8/16-dimensional filter state over the chunk sequence.
+ *   -core (DMMA) products of the discriminator stream with precomputed response tables (a streaming
+ *   kernel of independent warps), then parallel prefix scans of the filter states over the chunk
+ *   sequence in modal coordinates (independent 2x2 recurrences).
  *   Output: audio[n_frames][n_out][2] float32 (L == R, as in the reference).
  * PSS_PLAN_FIR (USB, LSB): 65-tap FIR on the I channel (the reference's hilbert() is an identity on
  *   the real part, USB == LSB) -> / max|.| * 0.95.          Output: audio[n_frames][N] float32 mono.
@@ -161,19 +162,19 @@ typedef struct {
     int kind;              /* PSS_PLAN_* */
     int mode;              /* PSS_MODE_* */
     int N;                 /* IQ samples per block */
-    /* --- PSS_PLAN_DECIM (see pyspecsdr_b200/filters.py: build_decim_plan) */
+    /* --- PSS_PLAN_DECIM (see pyspecsdr_b200/filters.py: build_decim_plan + build_modal_plan).  All tables are
+       in MODAL coordinates: the chunk-to-chunk transitions of the forward (pre-filter + Chebyshev forward
+       pass, SF states) and backward (Chebyshev reversed pass, SB = 8 states) recurrences are block-diagonal
+       with 2x2 real blocks. */
     int q, n_out, lead, SF, SB, n_body, m_tail, tail_start, tail_len;
-    int scan_block_f, scan_block_b;     /* block lengths of the forward / backward state scans */
     float scale, norm;
     int iq_correct;        /* WFM plans: 1 = iq_correction (signal_processing.py:46-80) fused in front of the
                               discriminator, which is what demodulate_signal does (:222-225); 0 = none, which
                               is demodulate_wfm called directly (:119-176) */
     const double* body;    /* [(SF+SB+1)][q+lead] response tables of one body chunk */
-    const double* AF;      /* [SF][SF]   forward state transition over one chunk */
-    const double* AFB;     /* [SF][SF]   AF ^ scan_block_f */
-    const double* AB;      /* [SB][SB]   backward state transition */
-    const double* ABB;     /* [SB][SB]   AB ^ scan_block_b */
-    const double* MB;      /* [SB][SF] */
+    const double* BF;      /* [SF/2][2][2] forward transition blocks */
+    const double* BB;      /* [SB/2][2][2] backward transition blocks */
+    const double* G;       /* [SB][SF]  backward forcing from the forward state */
     const double* CR;      /* [SF] */
     const double* CB;      /* [SB] */
     double DB;

@@ -42,9 +42,8 @@ class DemodDesc(_Sized):
         ("struct_size", C.c_size_t), ("kind", C.c_int), ("mode", C.c_int), ("N", C.c_int),
         ("q", C.c_int), ("n_out", C.c_int), ("lead", C.c_int), ("SF", C.c_int), ("SB", C.c_int),
         ("n_body", C.c_int), ("m_tail", C.c_int), ("tail_start", C.c_int), ("tail_len", C.c_int),
-        ("scan_block_f", C.c_int), ("scan_block_b", C.c_int),
         ("scale", C.c_float), ("norm", C.c_float), ("iq_correct", C.c_int),
-        ("body", _dp), ("AF", _dp), ("AFB", _dp), ("AB", _dp), ("ABB", _dp), ("MB", _dp), ("CR", _dp),
+        ("body", _dp), ("BF", _dp), ("BB", _dp), ("G", _dp), ("CR", _dp),
         ("CB", _dp), ("DB", C.c_double), ("head", _dp), ("tail_T", _dp), ("tail_M", _dp),
         ("taps", _dp), ("n_taps", C.c_int),
         ("sos", _dp), ("n_sections", C.c_int),

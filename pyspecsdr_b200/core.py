@@ -54,19 +54,16 @@ class DemodPlan:
 
         if mode in ("NFM", "WFM"):
             p = filters.build_decim_plan(mode, fs, N)
-            self.host_plan = p
+            m = filters.build_modal_plan(p)
+            self.host_plan, self.modal_plan = p, m
             desc.kind = 0
             for k in ("q", "n_out", "lead", "SF", "SB", "n_body", "m_tail", "tail_start", "tail_len"):
                 setattr(desc, k, int(getattr(p, k)))
-            desc.scan_block_f = max(1, -(-p.n_body // (256 // p.SF)))
-            desc.scan_block_b = max(1, -(-p.n_body // (256 // p.SB)))
-            desc.scale, desc.norm, desc.DB = np.float32(p.scale), p.norm, p.DB
+            desc.scale, desc.norm, desc.DB = np.float32(p.scale), p.norm, m.DB
             desc.iq_correct = 1 if (mode == "WFM" and iq_correct) else 0
-            desc.body, desc.AF, desc.AB, desc.MB = arr(p.body), arr(p.AF), arr(p.AB), arr(p.MB)
-            desc.AFB = arr(filters.matrix_power_seq(p.AF, desc.scan_block_f))
-            desc.ABB = arr(filters.matrix_power_seq(p.AB, desc.scan_block_b))
-            desc.CR, desc.CB = arr(p.CR), arr(p.CB)
-            desc.head, desc.tail_T, desc.tail_M = arr(p.head), arr(p.tail_T), arr(p.tail_M)
+            desc.body, desc.BF, desc.BB, desc.G = arr(m.body), arr(m.BF), arr(m.BB), arr(m.G)
+            desc.CR, desc.CB = arr(m.CR), arr(m.CB)
+            desc.head, desc.tail_T, desc.tail_M = arr(m.head), arr(m.tail_T), arr(m.tail_M)
         elif mode in ("USB", "LSB"):
             desc.kind = 1
             taps = filters.ssb_taps(fs)

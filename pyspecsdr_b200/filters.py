@@ -255,3 +255,173 @@ def emulate_decim(plan: DecimPlan, d: np.ndarray) -> np.ndarray:
         t = plan.AB @ t + plan.MB @ s[j] + u[j, SF:SF + SB]
     y[0] = plan.CB @ t + plan.DB * yf27
     return y
+
+
+# ------------------------------------------------------------------------------------------------
+# Modal form of the chunk recurrences (what the CUDA kernels run).
+#
+# The probed state transitions AF / AB are dense and badly scaled (DF2T cascade states of a filter whose
+# cut-off is 1/q of Nyquist differ by up to 1e12 in magnitude), which makes a chunk-to-chunk recurrence a
+# serial chain of dense matvecs.  Balancing (an exact power-of-two diagonal scaling) followed by an
+# eigen-decomposition turns them into independent 2x2 real blocks (one per complex-conjugate pole pair of
+# the chunk map, real poles in pairs): s = PF x with  x_{j+1} = blockdiag(BF) x_j + PF^-1 vF_j.
+# Independent 2x2 recurrences are parallel prefix scans, so nothing sequential is left on the GPU.
+# Measured conditioning of the eigenvector matrix after balancing: 60 ... 1.6e6 over 48 kS/s ... 61 MS/s,
+# i.e. the modal path agrees with the dense chunk-table form to 1e-9 ... 1e-14 (tests/test_host_logic.py).
+@dataclass
+class ModalPlan:
+    base: DecimPlan = field(repr=False)
+    body: np.ndarray = field(repr=False, default=None)    # [(SF+SB+1), q+lead] rows in modal coordinates
+    head: np.ndarray = field(repr=False, default=None)    # [(SF+1), 28]
+    tail_T: np.ndarray = field(repr=False, default=None)  # [(SB+m_tail), tail_len]
+    tail_M: np.ndarray = field(repr=False, default=None)  # [(SB+m_tail), SF]  (acts on the modal end state)
+    BF: np.ndarray = field(repr=False, default=None)      # [SF/2, 2, 2] forward blocks
+    BB: np.ndarray = field(repr=False, default=None)      # [SB/2, 2, 2] backward blocks
+    G: np.ndarray = field(repr=False, default=None)       # [SB, SF]  backward forcing from the forward state
+    CR: np.ndarray = field(repr=False, default=None)      # [SF]
+    CB: np.ndarray = field(repr=False, default=None)      # [SB]
+    DB: float = 0.0
+    cond_f: float = 0.0
+    cond_b: float = 0.0
+
+
+def _real_block_diagonalise(A: np.ndarray):
+    """A (even order) -> (P, blocks, cond) with A = P blockdiag(blocks) P^-1, real 2x2 blocks."""
+    from scipy import linalg as sl
+    n = A.shape[0]
+    Ab, (scale, _) = sl.matrix_balance(A, permute=False, separate=True)      # powers of two: exact
+    lam, V = np.linalg.eig(Ab)
+    tol = 1e-12 * max(1.0, float(np.max(np.abs(lam))))
+    used = np.zeros(n, bool)
+    cols, blocks, reals = [], [], []
+    for i in range(n):
+        if used[i]:
+            continue
+        if abs(lam[i].imag) <= tol:
+            reals.append(i)
+            used[i] = True
+            continue
+        # its conjugate partner
+        cand = [k for k in range(n) if not used[k] and k != i and abs(lam[k] - np.conj(lam[i])) <= 1e-8 * abs(lam[i])]
+        if not cand:
+            raise ValueError("unpaired complex eigenvalue in the chunk transition")
+        k = cand[0]
+        used[i] = used[k] = True
+        m = i if lam[i].imag > 0 else k
+        a, b = lam[m].real, lam[m].imag
+        cols += [V[:, m].real, V[:, m].imag]
+        blocks.append(np.array([[a, b], [-b, a]]))
+    if len(reals) % 2:
+        raise ValueError("odd number of real eigenvalues in the chunk transition")
+    reals.sort(key=lambda i: -abs(lam[i]))
+    for a, b in zip(reals[0::2], reals[1::2]):
+        cols += [V[:, a].real, V[:, b].real]
+        blocks.append(np.diag([lam[a].real, lam[b].real]))
+    P = np.stack(cols, axis=1)
+    cond = float(np.linalg.cond(P))
+    if not np.isfinite(cond) or cond > 1e9:
+        raise ValueError(f"chunk transition is not diagonalisable to working accuracy (cond {cond:.2e})")
+    Pf = scale[:, None] * P                                                   # undo the balancing
+    Pi = np.linalg.inv(P) / scale[None, :]
+    Bd = np.zeros((n, n))
+    for i, blk in enumerate(blocks):
+        Bd[2 * i:2 * i + 2, 2 * i:2 * i + 2] = blk
+    err = np.max(np.abs(Pf @ Bd @ Pi - A) / (np.abs(A) + np.max(np.abs(A)) * 1e-30 + 1e-300))
+    return Pf, Pi, np.array(blocks), cond, float(err)
+
+
+def build_modal_plan(plan: DecimPlan) -> ModalPlan:
+    SF, SB = plan.SF, plan.SB
+    PF, PFi, BF, cf, _ = _real_block_diagonalise(plan.AF)
+    PB, PBi, BB, cb, _ = _real_block_diagonalise(plan.AB)
+    body = np.vstack([PFi @ plan.body[:SF], PBi @ plan.body[SF:SF + SB], plan.body[SF + SB:]])
+    head = np.vstack([PFi @ plan.head[:SF], plan.head[SF:]])
+    tail_T = np.vstack([PBi @ plan.tail_T[:SB], plan.tail_T[SB:]])
+    tail_M = np.vstack([PBi @ plan.tail_M[:SB], plan.tail_M[SB:]]) @ PF
+    return ModalPlan(base=plan, body=body, head=head, tail_T=tail_T, tail_M=tail_M, BF=BF, BB=BB,
+                     G=PBi @ plan.MB @ PF, CR=plan.CR @ PF, CB=plan.CB @ PB, DB=plan.DB, cond_f=cf, cond_b=cb)
+
+
+SCAN_CPL = 10           # chunks per lane of the scan kernel
+SCAN_THREADS = 32       # one warp per block of audio -> 320 chunks per segment
+
+
+def _block_scan(blocks, x0, f):
+    """x_{i+1} = blockdiag(blocks) x_i + f_i by the kernel's scheme: threads own SCAN_CPL consecutive steps,
+    thread aggregates are combined by a Kogge-Stone scan inside groups of 32, group carries propagate with
+    the 32-group power.  Returns the states BEFORE every step [n, S] and the final state."""
+    n, S = f.shape
+    nb = S // 2
+    cpl, T = SCAN_CPL, SCAN_THREADS
+    before = np.zeros((n, S))
+    x_seg = np.array(x0, dtype=np.float64)
+    M = np.array([np.linalg.matrix_power(b, cpl) for b in blocks])
+    pw = [M]
+    for _ in range(5):
+        pw.append(np.einsum("bij,bjk->bik", pw[-1], pw[-1]))          # M^(2^s); pw[5] = M^32
+    lane = [np.stack([np.eye(2)] * nb)]
+    for _ in range(31):
+        lane.append(np.einsum("bij,bjk->bik", M, lane[-1]))          # M^l
+    mv = lambda Bs, v: np.einsum("bij,bj->bi", Bs, v.reshape(nb, 2)).reshape(S)
+    for base in range(0, n, cpl * T):
+        seg = np.zeros((T * cpl, S))
+        m = min(n - base, T * cpl)
+        seg[:m] = f[base:base + m]
+        e = np.zeros((T, S))
+        for p in range(T):
+            x = x_seg.copy() if p == 0 else np.zeros(S)
+            for c in range(cpl):
+                x = mv(blocks, x) + seg[p * cpl + c]
+            e[p] = x
+        inc = e.copy()
+        for s in range(5):
+            off = 1 << s
+            nxt = inc.copy()
+            for p in range(T):
+                if (p % 32) >= off:
+                    nxt[p] = inc[p] + mv(pw[s], inc[p - off])
+            inc = nxt
+        carry = np.zeros((T // 32, S))
+        for w in range(1, T // 32):
+            carry[w] = mv(pw[5], carry[w - 1]) + inc[32 * (w - 1) + 31]
+        for p in range(T):
+            w, l = divmod(p, 32)
+            X = mv(lane[l], carry[w]) + (inc[p - 1] if l > 0 else 0.0)
+            if p == 0:
+                X = x_seg.copy()
+            for c in range(cpl):
+                i = base + p * cpl + c
+                if i < n:
+                    before[i] = X
+                X = mv(blocks, X) + seg[p * cpl + c]
+                if i == n - 1:
+                    x_end = X.copy()
+        x_seg = mv(lane[31], mv(M, carry[T // 32 - 1])) + inc[T - 1]      # state after the whole segment
+    return before, x_end
+
+
+def emulate_decim_modal(mp: ModalPlan, d: np.ndarray) -> np.ndarray:
+    """numpy restatement of the two CUDA kernels (fp64): forcing dot products in modal coordinates, then the
+    forward and backward block scans, tail, outputs.  d = scaled discriminator samples [L]."""
+    plan = mp.base
+    q, lead, SF, SB, nbd = plan.q, plan.lead, plan.SF, plan.SB, plan.n_body
+    d = np.asarray(d, dtype=np.float64)
+    dpad = np.concatenate([np.zeros(lead), d])
+    hv = mp.head @ d[:EDGE + 1]
+    wins = np.stack([dpad[(j - 1) * q + 1:(j - 1) * q + 1 + q + lead] for j in range(1, nbd + 1)]) if nbd else np.zeros((0, q + lead))
+    u = wins @ mp.body.T                                        # kernel 1: [n_body, SF+SB+1]
+    zb, z_end = _block_scan(mp.BF, hv[:SF], u[:, :SF]) if nbd else (np.zeros((0, SF)), hv[:SF])
+    fb = u[:, SF:SF + SB] + zb @ mp.G.T                         # backward forcing of chunk j (uses z_j)
+    yfl = zb @ mp.CR + u[:, SF + SB]
+    ts = plan.tail_start + lead
+    tv = mp.tail_M @ z_end + mp.tail_T @ dpad[ts:ts + plan.tail_len]
+    # reversed order: step i handles chunk j = n_body - i; one extra zero-forcing step exposes t_1
+    fr = np.vstack([fb[::-1], np.zeros((1, SB))])
+    tb, _ = _block_scan(mp.BB, tv[:SB], fr)
+    y = np.zeros(plan.n_out)
+    y[nbd + 1:] = tv[SB:]
+    for i in range(nbd):
+        j = nbd - i
+        y[j] = mp.CB @ tb[i] + mp.DB * yfl[j - 1]
+    y[0] = mp.CB @ tb[nbd] + mp.DB * hv[SF]
+    return y

@@ -35,6 +35,29 @@ def test_decim_tables_reproduce_reference(mode, kind, n, fs):
     assert np.sqrt(np.mean((y - ref[:, 0]) ** 2)) < 1e-9
 
 
+@pytest.mark.parametrize("mode,kind,n,fs", [
+    ("NFM", "wbfm", 32768, 2.4e6), ("WFM", "wbfm", 32768, 2.4e6), ("WFM", "noise", 16385, 1.024e6),
+    ("NFM", "noise", 8192, 250e3), ("WFM", "wbfm", 32768, 20e6), ("NFM", "wbfm", 8192, 48e3)])
+def test_modal_form_and_block_scans_reproduce_reference(mode, kind, n, fs):
+    """What the two CUDA kernels run: tables in modal coordinates (balanced eigen-decomposition of the chunk
+    transitions into 2x2 real blocks) and the thread-blocked Kogge-Stone scans, emulated in numpy with the
+    kernel's own segment / lane scheme.  Must agree with the dense chunk-table form and with the reference."""
+    plan = filters.build_decim_plan(mode, fs, n)
+    mp = filters.build_modal_plan(plan)
+    assert mp.cond_f < 1e7 and mp.cond_b < 1e7
+    x = synth.make(kind, n, seed=11)
+    if mode == "WFM":
+        xc = O.iq_correct(x)
+        d = np.angle(xc[1:] * np.conj(xc[:-1]))
+    else:
+        d = np.angle(x[1:] * np.conj(x[:-1])) * (fs / (2 * np.pi))
+    y = filters.emulate_decim_modal(mp, d)
+    y0 = filters.emulate_decim(plan, d)
+    assert np.max(np.abs(y - y0)) <= 1e-8 * np.max(np.abs(y0))
+    ref = O.demod(x, fs, mode)
+    assert np.sqrt(np.mean((y / np.max(np.abs(y)) * plan.norm - ref[:, 0]) ** 2)) < 1e-8
+
+
 def test_decim_plan_geometry():
     p = filters.build_decim_plan("NFM", 2.4e6, 32768)
     assert (p.q, p.n_out, p.lead, p.SF, p.SB) == (108, 304, 64, 8, 8)
