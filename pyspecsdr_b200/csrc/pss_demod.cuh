@@ -7,7 +7,7 @@
 
 #define EDGE 27
 #define FORCE_THREADS 256        // forcing kernel: 8 independent warps per CTA
-#define SCAN_THREADS 128         // scan kernel: one WARP per block of audio, 4 warps per CTA
+#define SCAN_THREADS 256         // scan kernel: one CTA of 8 warps per block of audio
 #define SCAN_CPL 10              // chunks per lane of the scan kernel (32 * SCAN_CPL chunks per segment)
 #define WBUF_FLOATS 1088         // per-warp discriminator window of the forcing kernel
 #define SLAB_ROW 132             // row stride of the 8-row slab layout (== 4 mod 8: conflict-free A fragments)
@@ -17,13 +17,13 @@
 struct DecimDev {
     int mode, N, L, q, n_out, lead, SF, SB, n_body, m_tail, tail_start, tail_len;
     int Kp, KS, NTD, rows, CS;                  // NTD = (SF + SB) / 8 tensor n-tiles; CS = chunk stride of a scratch row
-    int tail_pad, scan_warps;
+    int tail_pad, scan_warps, scan_slot_smem;
     int groups;                                 // chunk groups of 8 per block
     int contiguous;                             // 1: one contiguous window per group; 0: 8 row slabs per k-slab
     int iq_correct;                             // WFM: 1 = iq_correction fused in front of the discriminator
     float scale, norm;
     int tab_in_smem;
-    int force_smem, scan_smem;                  // dynamic shared memory of the two kernels
+    int force_smem, scan_smem, fused_tab_smem;  // dynamic shared memory of the kernels (fused: 0 = table stays global)
     long long slot_doubles;                     // doubles of scratch per block: rows * CS
     const double *tabF;                         // fragment-ordered body table [KS][NTD][32] then the r row [KS][4]
     const double *head, *tailT, *tailM;
@@ -33,17 +33,15 @@ struct DecimDev {
 };
 
 // Packed scan tables (doubles), see pss_demod_decim.cu: for the forward (nf = SF/2 blocks) and backward
-// (nb = SB/2) recurrences: the 2x2 blocks B, M^(2^s) for s = 0..5 with M = B^SCAN_CPL, M^l for l = 0..31;
-// then G [SB][SF], CR [SF], CB [SB].
+// (nb = SB/2) recurrences: the 2x2 blocks B and M^(2^s) for s = 0..5 with M = B^SCAN_CPL; then G [SB][SF],
+// CR [SF], CB [SB].
 struct ScanTabLayout {
     int nf, nb;
     __host__ __device__ int BF() const { return 0; }
     __host__ __device__ int PWF() const { return BF() + nf * 4; }
-    __host__ __device__ int LNF() const { return PWF() + 6 * nf * 4; }
-    __host__ __device__ int BB() const { return LNF() + 32 * nf * 4; }
+    __host__ __device__ int BB() const { return PWF() + 6 * nf * 4; }
     __host__ __device__ int PWB() const { return BB() + nb * 4; }
-    __host__ __device__ int LNB() const { return PWB() + 6 * nb * 4; }
-    __host__ __device__ int G() const { return LNB() + 32 * nb * 4; }
+    __host__ __device__ int G() const { return PWB() + 6 * nb * 4; }
     __host__ __device__ int CR() const { return G() + 2 * nb * 2 * nf; }
     __host__ __device__ int CB() const { return CR() + 2 * nf; }
     __host__ __device__ int total() const { return CB() + 2 * nb; }

@@ -247,6 +247,141 @@ demod_force_kernel(const DecimDev D, const float2* __restrict__ iq, const int n_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ kernel 1, fused
+// The same products with the discriminator computed where the tensor-core fragment needs it: lane
+// (r = lane / 4, c = lane % 4) of k-step ks owns window sample r*q + 4*ks + c of chunk r, which is exactly
+// the A-fragment element of mma.m8n8k4.  Each lane loads ONE IQ sample per k-step (a depth-PD register
+// pipeline keeps PD loads in flight), corrects it once, and takes the later neighbour from lane c+1 or,
+// for c == 3, from the next k-step's sample of lane (r, 0).  No shared-memory window, no warp barrier,
+// any q; shared memory holds the response table only.
+template <int SF, bool EDGE_CHECK, bool TAB_SMEM, int DIAG, int UNR>
+__device__ __forceinline__ void force_unit_fused(const DecimDev& D, const float2* __restrict__ x, const int g0, const IqCorr kc,
+                                                 const double* __restrict__ tab, const double* __restrict__ trow,
+                                                 double (&c0)[(SF + 8) / 8], double (&c1)[(SF + 8) / 8], double& racc,
+                                                 const int lane) {
+    constexpr bool WFM = SF == 16;
+    constexpr int NTD = (SF + 8) / 8, PD = 6;
+    const int r = lane >> 2, c = lane & 3, KS = D.KS, N = D.N, L = D.N - 1;
+    const int e0 = r * D.q + c;
+    const float2* xp = x + g0 + e0;
+    auto load = [&](int ks) {
+        bool ok = ks <= KS;
+        if (EDGE_CHECK) {
+            const int gi = g0 + e0 + 4 * ks;
+            ok = ok && gi >= 0 && gi < N;
+        }
+        float2 v = make_float2(0.f, 0.f);
+        if (DIAG == 3) return make_float2(1.f + ks, 0.5f * lane);                   // DIAG 3: timing without the IQ loads
+        if (ok) v = __ldg(xp + 4 * ks);
+        return v;
+    };
+    float2 ring[PD];
+#pragma unroll
+    for (int i = 0; i < PD; ++i) ring[i] = load(i + 1);
+    // iq_correction (signal_processing.py:55-71) up to its positive common factor 1 / (q_amp * cos_phi), which a
+    // phase difference does not see: (I', Q') = (I / alpha, Q - sin_phi / alpha * I) -- two operations per sample
+    auto correct = [&](const float2 v) { return make_float2(__fmul_rn(kc.inv_a, v.x), __fmaf_rn(kc.g, v.x, v.y)); };
+    float2 S0 = load(0);
+    if (WFM) S0 = correct(S0);
+    const double* bp = tab + lane;
+    const double* tp = trow + c;
+    const int src0 = lane & ~3;
+    double racc1 = 0.0;
+#pragma unroll UNR
+    for (int ks = 0; ks < KS; ++ks) {
+        float2 S1 = ring[0];
+#pragma unroll
+        for (int i = 0; i + 1 < PD; ++i) ring[i] = ring[i + 1];
+        ring[PD - 1] = load(ks + PD + 1);
+        if (WFM) S1 = correct(S1);
+        float2 a, n;
+        a.x = __shfl_down_sync(0xffffffffu, S0.x, 1);
+        a.y = __shfl_down_sync(0xffffffffu, S0.y, 1);
+        n.x = __shfl_sync(0xffffffffu, S1.x, src0);
+        n.y = __shfl_sync(0xffffffffu, S1.y, src0);
+        if (c == 3) a = n;
+        float d = DIAG == 2 ? a.x + S0.y : disc_core<WFM>(a, S0, D.scale);      // DIAG 2: timing without the discriminator math
+        if (EDGE_CHECK) {
+            const int g = g0 + e0 + 4 * ks;
+            if (g < 0 || g >= L) d = 0.f;
+        }
+        const double av = (double)d;
+#pragma unroll
+        for (int nt = 0; nt < NTD; ++nt) {
+            double b;
+            if (TAB_SMEM) b = bp[(ks * NTD + nt) * 32];
+            else b = __ldg(bp + (ks * NTD + nt) * 32);
+            if (DIAG == 1) c0[nt] = fma(av, b, c0[nt]);                             // DIAG 1: timing without the tensor pipe
+            else dmma_m8n8k4(c0[nt], c1[nt], av, b);
+        }
+        if (ks & 1) racc1 = fma(av, TAB_SMEM ? tp[4 * ks] : __ldg(tp + 4 * ks), racc1);
+        else racc = fma(av, TAB_SMEM ? tp[4 * ks] : __ldg(tp + 4 * ks), racc);
+        S0 = S1;
+    }
+    racc += racc1;
+}
+
+template <int SF, bool TAB_SMEM, int DIAG = 0, int UNR = 4, int MINB = 3>
+__global__ void __launch_bounds__(FORCE_THREADS, MINB)
+demod_force_fused_kernel(const DecimDev D, const float2* __restrict__ iq, const int n_frames, double* __restrict__ F,
+                         const float4* __restrict__ corr) {
+    constexpr bool WFM = SF == 16;
+    constexpr int SB = 8, NTD = (SF + SB) / 8, RROW = SF + SB;
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* tab = D.tabF;
+    if (TAB_SMEM) {
+        double* ts = reinterpret_cast<double*>(smem);
+        const int n = D.KS * (NTD * 32 + 4);
+        for (int i = tid; i < n; i += FORCE_THREADS) ts[i] = D.tabF[i];
+        tab = ts;
+        __syncthreads();
+    }
+    const double* trow = tab + (size_t)D.KS * NTD * 32;               // [KS][4]: r-row taps
+    const int q = D.q, groups = D.groups, CS = D.CS;
+    const int n_units = n_frames * groups;
+    const int wstride = gridDim.x * (FORCE_THREADS / 32);
+    for (int unit = blockIdx.x * (FORCE_THREADS / 32) + warp; unit < n_units; unit += wstride) {
+        const int frame = unit / groups;
+        const int g = unit - frame * groups;
+        const float2* x = iq + (long long)frame * D.N;
+        IqCorr kc = {1.f, 1.f, 0.f, 1.f};
+        if (WFM && D.iq_correct) {
+            const float4 cf = __ldg(corr + frame);
+            kc = {cf.x, cf.y, cf.z, cf.w};
+        }
+        const int g0 = 8 * g * q + 1 - D.lead;                        // first discriminator index of the group
+        if (DIAG != 4 && unit + wstride < n_units) {
+            // pull the warp's NEXT window into L2 as whole 128-byte lines while this one is consumed 32 bytes
+            // per row and k-step (the next unit of a warp is wstride units ahead: another block, same group)
+            const int nu = unit + wstride, nfr = nu / groups, ng = nu - nfr * groups;
+            const char* nb = reinterpret_cast<const char*>(iq + (long long)nfr * D.N + max(8 * ng * q + 1 - D.lead, 0));
+            const int bytes = min((7 * q + 4 * D.KS + 4) * 8, (D.N - max(8 * ng * q + 1 - D.lead, 0)) * 8);
+            for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
+        }
+        double c0[NTD], c1[NTD], racc = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NTD; ++nt) c0[nt] = c1[nt] = 0.0;
+        if (g0 >= 0 && g0 + 7 * q + 4 * D.KS + 4 < D.N)
+            force_unit_fused<SF, false, TAB_SMEM, DIAG, UNR>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
+        else
+            force_unit_fused<SF, true, TAB_SMEM, DIAG, UNR>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
+        racc += __shfl_xor_sync(0xffffffffu, racc, 1);
+        racc += __shfl_xor_sync(0xffffffffu, racc, 2);
+        const int c = 8 * g + (lane >> 2);                            // chunk index (body chunk j = c + 1)
+        if (c < D.n_body) {
+            double* col = F + (long long)frame * D.slot_doubles + c;
+#pragma unroll
+            for (int nt = 0; nt < NTD; ++nt) {
+                const int row = nt * 8 + 2 * (lane & 3);
+                col[(long long)row * CS] = c0[nt];
+                col[(long long)(row + 1) * CS] = c1[nt];
+            }
+            if ((lane & 3) == 0) col[(long long)RROW * CS] = racc;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel 2
 __device__ __forceinline__ void mv2(const double* __restrict__ B, const double x0, const double x1, double& y0,
                                     double& y1) {
@@ -295,8 +430,36 @@ __device__ __forceinline__ void lane_scan(const double (&f0)[SCAN_CPL], const do
 
 // One CTA of 4 warps per block of audio.  The 2x2 recurrences are independent, so every warp scans its own
 // ones without talking to the others; CTA barriers only separate the phases.
-template <int SF>
-__global__ void __launch_bounds__(SCAN_THREADS, 4)
+// TMA bulk copy (cp.async.bulk, SASS UBLKCP) of one block's scratch into shared memory, completion on an mbarrier.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, const unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, const unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, const unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, const unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// SLOT_SMEM: the block's whole scratch (rows x CS doubles, ~60 KB at the bench geometry) is pulled into shared
+// memory by one TMA bulk copy while the head / tail discriminator samples are computed, every phase then
+// runs at shared-memory latency and nothing is written back (only the audio leaves).  Blocks whose scratch
+// does not fit keep it in global memory (L2).
+template <int SF, bool SLOT_SMEM>
+__global__ void __launch_bounds__(SCAN_THREADS, 3)
 demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __restrict__ audio, const int n_frames,
                   double* __restrict__ F, const float4* __restrict__ corr) {
     constexpr bool WFM = SF == 16;
@@ -308,24 +471,38 @@ demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __rest
     double* tres = zend + SF;                                         // [64]  tail result: backward start state, last outputs
     double* dh = tres + 64;                                           // [28]  head discriminator samples
     double* t1 = dh + 28;                                             // [SB]  backward state after chunk 0
-    double* red = t1 + SB;                                            // [8]   [0..3] warp maxima, [4] yf at ext index 27
-    float* tile = reinterpret_cast<float*>(red + 8);                  // [tail_len] tail discriminator samples
+    double* red = t1 + SB;                                            // [16]  [0..7] warp maxima, [8] yf at ext index 27
+    float* tile = reinterpret_cast<float*>(red + 16);                 // [tail_pad] tail discriminator samples
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(tile + D.tail_pad);
+    double* Fs = reinterpret_cast<double*>(bar + 2);                  // [rows][CS] (SLOT_SMEM)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ScanTabLayout T{NF, NBK};
     for (int i = tid; i < D.scan_tab_doubles; i += SCAN_THREADS) tabs[i] = D.scanTab[i];
+    if (SLOT_SMEM && tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    unsigned phase = 0;
     const double *Gm = tabs + T.G(), *CR = tabs + T.CR(), *CB = tabs + T.CB();
     const double *BF = tabs + T.BF(), *PWF = tabs + T.PWF(), *BBk = tabs + T.BB(), *PWB = tabs + T.PWB();
     const int nbd = D.n_body, L = D.L, CS = D.CS;
 
     for (int frame = blockIdx.x; frame < n_frames; frame += gridDim.x) {
         const float2* x = iq + (long long)frame * D.N;
-        double* Fb = F + (long long)frame * D.slot_doubles;
+        double* Fb = SLOT_SMEM ? Fs : F + (long long)frame * D.slot_doubles;
+        __syncthreads();                                              // the previous block is done with Fs / bar
+        if (SLOT_SMEM && tid == 0) {
+            const unsigned bytes = (unsigned)(D.slot_doubles * 8);
+            mbar_expect_tx(bar, bytes);
+            const char* src = reinterpret_cast<const char*>(F + (long long)frame * D.slot_doubles);
+            for (unsigned o = 0; o < bytes; o += 32768u)              // bulk copies of <= 32 KB
+                bulk_g2s(reinterpret_cast<char*>(Fs) + o, src + o, min(32768u, bytes - o), bar);
+        }
         IqCorr kc = {1.f, 1.f, 0.f, 1.f};
         if (WFM && D.iq_correct) {
             const float4 c = __ldg(corr + frame);
             kc = {c.x, c.y, c.z, c.w};
         }
-        __syncthreads();
         // ---- head: ext[0..27] depends on d[0..27] only; tail window
         if (tid <= EDGE) dh[tid] = (double)discriminator<WFM>(x, tid, L, kc, D.scale);
         for (int i = tid; i < D.tail_len; i += SCAN_THREADS) tile[i] = discriminator<WFM>(x, D.tail_start + i, L, kc, D.scale);
@@ -334,7 +511,11 @@ demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __rest
             double acc = 0.0;
             for (int i = 0; i <= EDGE; ++i) acc = fma(D.head[tid * (EDGE + 1) + i], dh[i], acc);
             if (tid < SF) zs[tid] = acc;             // modal state entering chunk 1
-            else red[4] = acc;                       // yf at ext index 27
+            else red[8] = acc;                       // yf at ext index 27
+        }
+        if (SLOT_SMEM) {
+            mbar_wait(bar, phase);                   // the forcing rows have landed
+            phase ^= 1;
         }
         __syncthreads();
 
@@ -357,11 +538,12 @@ demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __rest
                 }
                 double X0, X1;
                 lane_scan<true>(f0, f1, s0, s1, X0, X1, BF + 4 * b, PWF + 4 * b, NF * 4, lane);
-                double z0[CPL], z1[CPL];
 #pragma unroll
                 for (int i = 0; i < CPL; ++i) {
-                    z0[i] = X0;
-                    z1[i] = X1;
+                    if (c0 + i < nbd) {
+                        r0[i] = X0;
+                        r1[i] = X1;
+                    }
                     double y0, y1;
                     mv2(BF + 4 * b, X0, X1, y0, y1);
                     X0 = y0 + f0[i];
@@ -371,12 +553,6 @@ demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __rest
                         zend[2 * b + 1] = X1;
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < CPL; i += 2)
-                    if (c0 + i < nbd) {                               // the pad chunk of an odd n_body is scratch
-                        *reinterpret_cast<double2*>(r0 + i) = make_double2(z0[i], z0[i + 1]);
-                        *reinterpret_cast<double2*>(r1 + i) = make_double2(z1[i], z1[i + 1]);
-                    }
             }
             if (nbd == 0 && lane == 0) {
                 zend[2 * b] = s0;
@@ -387,9 +563,18 @@ demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __rest
 
         // ---- tail block: backward state entering chunk n_body, and the last m_tail outputs
         for (int rr = warp; rr < SB + D.m_tail; rr += NW) {
-            double acc = 0.0;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
             const double* tr = D.tailT + (size_t)rr * D.tail_len;
-            for (int i = lane; i < D.tail_len; i += 32) acc = fma(tr[i], (double)tile[i], acc);
+            int i = lane;
+            for (; i + 96 < D.tail_len; i += 128) {                  // four loads in flight
+                const double t0 = tr[i], t1v = tr[i + 32], t2 = tr[i + 64], t3 = tr[i + 96];
+                a0 = fma(t0, (double)tile[i], a0);
+                a1 = fma(t1v, (double)tile[i + 32], a1);
+                a2 = fma(t2, (double)tile[i + 64], a2);
+                a3 = fma(t3, (double)tile[i + 96], a3);
+            }
+            for (; i < D.tail_len; i += 32) a0 = fma(tr[i], (double)tile[i], a0);
+            double acc = (a0 + a1) + (a2 + a3);
             if (lane < SF) acc = fma(D.tailM[rr * SF + lane], zend[lane], acc);
             acc = warp_sum(acc);
             if (lane == 0) tres[rr] = acc;
@@ -466,7 +651,7 @@ demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __rest
             col[(long long)RROW * CS] = y;
             mx = fmax(mx, fabs(y));
         }
-        double y_first = D.DB * red[4];
+        double y_first = D.DB * red[8];
 #pragma unroll
         for (int k = 0; k < SB; ++k) y_first = fma(CB[k], t1[k], y_first);
         mx = fmax(mx, fabs(y_first));
@@ -475,7 +660,9 @@ demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __rest
         for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
         if (lane == 0) red[warp] = mx;
         __syncthreads();                                              // also orders the y stores above
-        mx = fmax(fmax(red[0], red[1]), fmax(red[2], red[3]));
+        mx = red[0];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) mx = fmax(mx, red[w]);
         const double gain = (double)D.norm / mx;                     // audio / max|audio| * 0.95 (:115)
         float2* dst = reinterpret_cast<float2*>(audio) + (long long)frame * D.n_out;
         for (int k = tid; k < D.n_out; k += SCAN_THREADS) {
@@ -493,7 +680,7 @@ static void mat2_mul(const double* a, const double* b, double* c) {
     memcpy(c, r, sizeof r);
 }
 
-static void fill_scan_tables(const double* blocks, int nb, double* B, double* PW, double* LN) {
+static void fill_scan_tables(const double* blocks, int nb, double* B, double* PW) {
     for (int b = 0; b < nb; ++b) {
         const double* blk = blocks + 4 * b;
         memcpy(B + 4 * b, blk, 32);
@@ -504,11 +691,6 @@ static void fill_scan_tables(const double* blocks, int nb, double* B, double* PW
         for (int s = 0; s < 6; ++s) {                                 // M^(2^s)
             memcpy(PW + (s * nb + b) * 4, P, 32);
             mat2_mul(P, P, P);
-        }
-        double Lm[4] = {1, 0, 0, 1};
-        for (int l = 0; l < 32; ++l) {                                // M^l
-            memcpy(LN + (l * nb + b) * 4, Lm, 32);
-            mat2_mul(M, Lm, Lm);
         }
     }
 }
@@ -549,8 +731,8 @@ int pss_decim_create(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* pl) 
     }
     const ScanTabLayout T{D.SF / 2, D.SB / 2};
     std::vector<double> st(T.total(), 0.0);
-    fill_scan_tables(d->BF, T.nf, &st[T.BF()], &st[T.PWF()], &st[T.LNF()]);
-    fill_scan_tables(d->BB, T.nb, &st[T.BB()], &st[T.PWB()], &st[T.LNB()]);
+    fill_scan_tables(d->BF, T.nf, &st[T.BF()], &st[T.PWF()]);
+    fill_scan_tables(d->BB, T.nb, &st[T.BB()], &st[T.PWB()]);
     memcpy(&st[T.G()], d->G, (size_t)D.SB * D.SF * 8);
     memcpy(&st[T.CR()], d->CR, (size_t)D.SF * 8);
     memcpy(&st[T.CB()], d->CB, (size_t)D.SB * 8);
@@ -566,23 +748,72 @@ int pss_decim_create(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* pl) 
     const size_t wb = (size_t)(FORCE_THREADS / 32) * WBUF_FLOATS * 4, tb = frag.size() * 8;
     D.tab_in_smem = wb + tb <= 72 * 1024;
     D.force_smem = (int)(wb + (D.tab_in_smem ? tb : 0));
-    // scan kernel: one CTA per block of audio
-    const size_t ss = (size_t)(D.scan_tab_doubles + 2 * D.SF + 64 + 28 + 8 + 8) * 8 + (size_t)D.tail_pad * 4 + 16;
+    D.fused_tab_smem = tb <= 72 * 1024 ? (int)tb : 0;              // fused kernel: the table alone
+    // scan kernel: one CTA per block of audio; the block's scratch in shared memory when 3 CTAs / SM still fit
+    const size_t ss = (size_t)(D.scan_tab_doubles + 2 * D.SF + 64 + 28 + 8 + 16) * 8 + (size_t)D.tail_pad * 4 + 16 + 16;
     if (ss > 200 * 1024) return PSS_ERR_UNSUPPORTED;
-    D.scan_smem = (int)ss;
+    const size_t slot_b = (size_t)D.slot_doubles * 8;
+    D.scan_slot_smem = ss + slot_b <= 74 * 1024;
+    D.scan_smem = (int)(ss + (D.scan_slot_smem ? slot_b : 0));
     D.scan_warps = SCAN_THREADS / 32;
     pl->out_len = D.n_out;
     pl->channels = 2;
     return PSS_OK;
 }
 
+// PSS_DEMOD_FORCE=window selects the shared-memory-window variant of the forcing kernel (kept for comparison,
+// DESIGN.md 4); the default is the fused register-pipelined one.
+static bool use_window_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PSS_DEMOD_FORCE");
+        v = (e && !strcmp(e, "window")) ? 1 : 0;
+    }
+    return v == 1;
+}
+
 template <int SF>
 static int launch_sub(pss_ctx* ctx, pss_demod_plan* pl, const float2* iq, long long nf, float* audio, const float4* corr) {
     DecimDev& D = pl->dec;
     auto kf = demod_force_kernel<SF>;
-    auto ks = demod_scan_kernel<SF>;
-    PSS_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, D.force_smem));
+    auto ks = D.scan_slot_smem ? demod_scan_kernel<SF, true> : demod_scan_kernel<SF, false>;
     PSS_CUDA(ctx, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, D.scan_smem));
+    if (!use_window_variant()) {
+        if (nf * D.groups > 0x7fffffffLL) return PSS_ERR_UNSUPPORTED;
+        const long long units = nf * D.groups;
+        long long g1 = (units + FORCE_THREADS / 32 - 1) / (FORCE_THREADS / 32);
+        if (g1 > 3LL * ctx->sm_count) g1 = 3LL * ctx->sm_count;
+        const int tb = D.fused_tab_smem;
+        if (g1 > 0) {
+            static const int diag = getenv("PSS_DIAG") ? atoi(getenv("PSS_DIAG")) : 0;   // timing-only builds, wrong results
+            static const int var = getenv("PSS_FORCE_VARIANT") ? atoi(getenv("PSS_FORCE_VARIANT")) : 0;   // tuning experiments
+            if (tb && var) {
+                auto k = var == 1 ? demod_force_fused_kernel<SF, true, 0, 9, 3> : var == 2 ? demod_force_fused_kernel<SF, true, 0, 9, 2>
+                         : var == 3 ? demod_force_fused_kernel<SF, true, 0, 4, 4> : demod_force_fused_kernel<SF, true, 0, 3, 4>;
+                PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
+                long long gv = (var == 2 ? 2LL : var >= 3 ? 4LL : 3LL) * ctx->sm_count;
+                if (gv > g1) gv = g1;
+                k<<<(unsigned)gv, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, (double*)pl->F_scratch, corr);
+            } else if (tb && diag) {
+                auto k = diag == 1 ? demod_force_fused_kernel<SF, true, 1> : diag == 2 ? demod_force_fused_kernel<SF, true, 2>
+                         : diag == 3 ? demod_force_fused_kernel<SF, true, 3> : demod_force_fused_kernel<SF, true, 4>;
+                PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
+                k<<<(unsigned)g1, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, (double*)pl->F_scratch, corr);
+            } else if (tb) {
+                auto k = demod_force_fused_kernel<SF, true>;
+                PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
+                k<<<(unsigned)g1, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, (double*)pl->F_scratch, corr);
+            } else {
+                demod_force_fused_kernel<SF, false><<<(unsigned)g1, FORCE_THREADS, 0, ctx->stream>>>(D, iq, (int)nf, (double*)pl->F_scratch, corr);
+            }
+            PSS_LAUNCH_CHECK(ctx);
+        }
+        long long g2 = nf < 16LL * ctx->sm_count ? nf : 16LL * ctx->sm_count;
+        ks<<<(unsigned)g2, SCAN_THREADS, D.scan_smem, ctx->stream>>>(D, iq, audio, (int)nf, (double*)pl->F_scratch, corr);
+        PSS_LAUNCH_CHECK(ctx);
+        return PSS_OK;
+    }
+    PSS_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, D.force_smem));
     if (nf * D.groups > 0x7fffffffLL) return PSS_ERR_UNSUPPORTED;
     const long long units = nf * D.groups;
     long long g1 = (units + FORCE_THREADS / 32 - 1) / (FORCE_THREADS / 32);
