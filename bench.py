@@ -522,7 +522,8 @@ def main():
     moments = torch.empty(F, 4, device=dev, dtype=torch.float64)     # PSD by-product consumed by the WFM demod
     torch.cuda.synchronize()
 
-    names = ["psd_kernel<12,f64,smooth>", "display_render_kernel", f"demod_decim_kernel<{args.mode}>"]
+    names = ["psd_kernel<12,f64,smooth>", "display_render_kernel",
+             f"demod_corr + demod_force_fused + demod_scan kernels <{args.mode}>"]
 
     def step(ev=None):
         if ev is not None:

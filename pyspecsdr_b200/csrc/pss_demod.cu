@@ -526,6 +526,14 @@ void pss_demod_plan_destroy(pss_ctx* ctx, pss_demod_plan* pl) {
     }
     for (void* p : pl->dev_allocs) cudaFree(p);
     cudaFree(pl->F_scratch);
+    if (pl->side) {
+        cudaStreamSynchronize(pl->side);
+        cudaStreamDestroy(pl->side);
+        for (int i = 0; i < 2; ++i) {
+            cudaEventDestroy(pl->ev_force[i]);
+            cudaEventDestroy(pl->ev_scan[i]);
+        }
+    }
     cudaFree(pl->corr);
     cudaFree(pl->mom_scratch);
     cudaFree(pl->tile_scratch);

@@ -69,6 +69,8 @@ struct pss_demod_plan {
     size_t corr_bytes = 0;
     void* mom_scratch = nullptr;        // per-block I/Q second moments when the caller supplies none
     size_t mom_scratch_bytes = 0;
+    cudaStream_t side = nullptr;        // scan kernels of sub-batch k overlap the forcing kernel of k+1
+    cudaEvent_t ev_force[2] = {nullptr, nullptr}, ev_scan[2] = {nullptr, nullptr};
     void* tile_scratch = nullptr;       // per-block max|y| of tiled FIR plans
     size_t tile_scratch_bytes = 0;
 };

@@ -773,57 +773,50 @@ static bool use_window_variant() {
 }
 
 template <int SF>
-static int launch_sub(pss_ctx* ctx, pss_demod_plan* pl, const float2* iq, long long nf, float* audio, const float4* corr) {
+static int launch_force(pss_ctx* ctx, pss_demod_plan* pl, const float2* iq, long long nf, double* F, const float4* corr,
+                        bool beside_scan) {
     DecimDev& D = pl->dec;
-    auto kf = demod_force_kernel<SF>;
-    auto ks = D.scan_slot_smem ? demod_scan_kernel<SF, true> : demod_scan_kernel<SF, false>;
-    PSS_CUDA(ctx, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, D.scan_smem));
-    if (!use_window_variant()) {
-        if (nf * D.groups > 0x7fffffffLL) return PSS_ERR_UNSUPPORTED;
-        const long long units = nf * D.groups;
-        long long g1 = (units + FORCE_THREADS / 32 - 1) / (FORCE_THREADS / 32);
-        if (g1 > 3LL * ctx->sm_count) g1 = 3LL * ctx->sm_count;
-        const int tb = D.fused_tab_smem;
-        if (g1 > 0) {
-            static const int diag = getenv("PSS_DIAG") ? atoi(getenv("PSS_DIAG")) : 0;   // timing-only builds, wrong results
-            static const int var = getenv("PSS_FORCE_VARIANT") ? atoi(getenv("PSS_FORCE_VARIANT")) : 0;   // tuning experiments
-            if (tb && var) {
-                auto k = var == 1 ? demod_force_fused_kernel<SF, true, 0, 9, 3> : var == 2 ? demod_force_fused_kernel<SF, true, 0, 9, 2>
-                         : var == 3 ? demod_force_fused_kernel<SF, true, 0, 4, 4> : demod_force_fused_kernel<SF, true, 0, 3, 4>;
-                PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
-                long long gv = (var == 2 ? 2LL : var >= 3 ? 4LL : 3LL) * ctx->sm_count;
-                if (gv > g1) gv = g1;
-                k<<<(unsigned)gv, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, (double*)pl->F_scratch, corr);
-            } else if (tb && diag) {
-                auto k = diag == 1 ? demod_force_fused_kernel<SF, true, 1> : diag == 2 ? demod_force_fused_kernel<SF, true, 2>
-                         : diag == 3 ? demod_force_fused_kernel<SF, true, 3> : demod_force_fused_kernel<SF, true, 4>;
-                PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
-                k<<<(unsigned)g1, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, (double*)pl->F_scratch, corr);
-            } else if (tb) {
-                auto k = demod_force_fused_kernel<SF, true>;
-                PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
-                k<<<(unsigned)g1, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, (double*)pl->F_scratch, corr);
-            } else {
-                demod_force_fused_kernel<SF, false><<<(unsigned)g1, FORCE_THREADS, 0, ctx->stream>>>(D, iq, (int)nf, (double*)pl->F_scratch, corr);
-            }
-            PSS_LAUNCH_CHECK(ctx);
-        }
-        long long g2 = nf < 16LL * ctx->sm_count ? nf : 16LL * ctx->sm_count;
-        ks<<<(unsigned)g2, SCAN_THREADS, D.scan_smem, ctx->stream>>>(D, iq, audio, (int)nf, (double*)pl->F_scratch, corr);
-        PSS_LAUNCH_CHECK(ctx);
-        return PSS_OK;
-    }
-    PSS_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, D.force_smem));
     if (nf * D.groups > 0x7fffffffLL) return PSS_ERR_UNSUPPORTED;
     const long long units = nf * D.groups;
     long long g1 = (units + FORCE_THREADS / 32 - 1) / (FORCE_THREADS / 32);
-    if (g1 > 3LL * ctx->sm_count) g1 = 3LL * ctx->sm_count;
-    if (g1 > 0) {
-        kf<<<(unsigned)g1, FORCE_THREADS, D.force_smem, ctx->stream>>>(D, iq, (int)nf, (double*)pl->F_scratch, corr);
+    if (g1 < 1) return PSS_OK;
+    if (use_window_variant()) {
+        auto kf = demod_force_kernel<SF>;
+        PSS_CUDA(ctx, cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, D.force_smem));
+        if (g1 > 3LL * ctx->sm_count) g1 = 3LL * ctx->sm_count;
+        kf<<<(unsigned)g1, FORCE_THREADS, D.force_smem, ctx->stream>>>(D, iq, (int)nf, F, corr);
         PSS_LAUNCH_CHECK(ctx);
+        return PSS_OK;
     }
+    // 2 CTAs / SM when a scan kernel shares the SMs (its CTA needs the third slot's registers), else 3
+    const long long per_sm = beside_scan ? 2 : 3;
+    if (g1 > per_sm * ctx->sm_count) g1 = per_sm * ctx->sm_count;
+    const int tb = D.fused_tab_smem;
+    static const int diag = getenv("PSS_DIAG") ? atoi(getenv("PSS_DIAG")) : 0;   // timing-only builds, wrong results
+    if (tb && diag) {
+        auto k = diag == 1 ? demod_force_fused_kernel<SF, true, 1> : diag == 2 ? demod_force_fused_kernel<SF, true, 2>
+                 : diag == 3 ? demod_force_fused_kernel<SF, true, 3> : demod_force_fused_kernel<SF, true, 4>;
+        PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
+        k<<<(unsigned)g1, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, F, corr);
+    } else if (tb) {
+        auto k = demod_force_fused_kernel<SF, true>;
+        PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
+        k<<<(unsigned)g1, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, F, corr);
+    } else {
+        demod_force_fused_kernel<SF, false><<<(unsigned)g1, FORCE_THREADS, 0, ctx->stream>>>(D, iq, (int)nf, F, corr);
+    }
+    PSS_LAUNCH_CHECK(ctx);
+    return PSS_OK;
+}
+
+template <int SF>
+static int launch_scan(pss_ctx* ctx, pss_demod_plan* pl, const float2* iq, long long nf, float* audio, double* F,
+                       const float4* corr, cudaStream_t st) {
+    DecimDev& D = pl->dec;
+    auto ks = D.scan_slot_smem ? demod_scan_kernel<SF, true> : demod_scan_kernel<SF, false>;
+    PSS_CUDA(ctx, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, D.scan_smem));
     long long g2 = nf < 16LL * ctx->sm_count ? nf : 16LL * ctx->sm_count;
-    ks<<<(unsigned)g2, SCAN_THREADS, D.scan_smem, ctx->stream>>>(D, iq, audio, (int)nf, (double*)pl->F_scratch, corr);
+    ks<<<(unsigned)g2, SCAN_THREADS, D.scan_smem, st>>>(D, iq, audio, (int)nf, F, corr);
     PSS_LAUNCH_CHECK(ctx);
     return PSS_OK;
 }
@@ -832,12 +825,26 @@ int pss_decim_launch(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t 
                      const double* moments, int mom_fpb) {
     DecimDev& D = pl->dec;
     int rc;
-    // blocks per sub-batch: the forcing scratch of a sub-batch stays in L2 (<= ~40 MB), at least one wave of CTAs
+    // Sub-batches: the forcing scratch of a sub-batch stays in L2 (<= 40 MB) between the forcing kernel and
+    // the scan kernel, both on the context's stream.
+    // PSS_DEMOD_OVERLAP=1 (measured, not the default: 0.95 / 1.12 ms per GiB NFM / WFM against 0.75 / 0.86
+    // serial): two half-size scratch buffers, the scan kernel of sub-batch k on a side stream beside the
+    // forcing kernel of sub-batch k+1 at 2 CTAs / SM.
     const size_t slot_b = (size_t)D.slot_doubles * 8;
-    long long sub = (long long)((40u << 20) / slot_b);
+    static const bool want_overlap = getenv("PSS_DEMOD_OVERLAP") != nullptr;
+    long long sub = (long long)(((want_overlap ? 20u : 40u) << 20) / slot_b);
     if (sub < 1) sub = 1;
     if (sub > n_frames) sub = n_frames;
-    if ((rc = pss_reserve(ctx, &pl->F_scratch, &pl->F_scratch_bytes, (size_t)sub * slot_b))) return rc;
+    const bool overlap = want_overlap && n_frames > sub && !use_window_variant();
+    const size_t buf_b = (size_t)sub * slot_b;
+    if ((rc = pss_reserve(ctx, &pl->F_scratch, &pl->F_scratch_bytes, (overlap ? 2 : 1) * buf_b))) return rc;
+    if (overlap && !pl->side) {
+        PSS_CUDA(ctx, cudaStreamCreateWithFlags(&pl->side, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            PSS_CUDA(ctx, cudaEventCreateWithFlags(&pl->ev_force[i], cudaEventDisableTiming));
+            PSS_CUDA(ctx, cudaEventCreateWithFlags(&pl->ev_scan[i], cudaEventDisableTiming));
+        }
+    }
     const float4* corr = nullptr;
     if (D.SF == 16 && D.iq_correct) {
         if ((rc = pss_reserve(ctx, &pl->corr, &pl->corr_bytes, (size_t)n_frames * 16))) return rc;
@@ -854,12 +861,30 @@ int pss_decim_launch(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t 
         PSS_LAUNCH_CHECK(ctx);
         corr = (const float4*)pl->corr;
     }
-    for (int64_t f0 = 0; f0 < n_frames; f0 += sub) {
+    int k = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += sub, ++k) {
         const long long nf = n_frames - f0 < sub ? n_frames - f0 : sub;
         const float2* x = (const float2*)iq + f0 * D.N;
         float* a = audio + f0 * D.n_out * 2;
-        rc = D.SF == 8 ? launch_sub<8>(ctx, pl, x, nf, a, corr) : launch_sub<16>(ctx, pl, x, nf, a, corr ? corr + f0 : nullptr);
+        const int b = overlap ? (k & 1) : 0;
+        double* Fbuf = (double*)((char*)pl->F_scratch + (size_t)b * buf_b);
+        const float4* cr = corr ? corr + f0 : nullptr;
+        if (overlap && k >= 2) PSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pl->ev_scan[b], 0));     // buffer b is free again
+        rc = D.SF == 8 ? launch_force<8>(ctx, pl, x, nf, Fbuf, cr, overlap) : launch_force<16>(ctx, pl, x, nf, Fbuf, cr, overlap);
         if (rc) return rc;
+        cudaStream_t ss = ctx->stream;
+        if (overlap) {
+            PSS_CUDA(ctx, cudaEventRecord(pl->ev_force[b], ctx->stream));
+            PSS_CUDA(ctx, cudaStreamWaitEvent(pl->side, pl->ev_force[b], 0));
+            ss = pl->side;
+        }
+        rc = D.SF == 8 ? launch_scan<8>(ctx, pl, x, nf, a, Fbuf, cr, ss) : launch_scan<16>(ctx, pl, x, nf, a, Fbuf, cr, ss);
+        if (rc) return rc;
+        if (overlap) PSS_CUDA(ctx, cudaEventRecord(pl->ev_scan[b], pl->side));
+    }
+    if (overlap) {                                   // join: the caller's stream sees every scan finished
+        PSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pl->ev_scan[0], 0));
+        if (k >= 2) PSS_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, pl->ev_scan[1], 0));
     }
     return PSS_OK;
 }

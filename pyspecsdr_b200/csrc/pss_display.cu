@@ -122,18 +122,24 @@ __global__ void __launch_bounds__(256) display_render_kernel(const RenderArgs<T>
     }
     const long long base = r * (long long)R * W;
     const int total = R * W;
+    const float lo_f = (float)lo, range_f = (float)range;
+    int y = threadIdx.x / W, c = threadIdx.x - y * W;                 // (row, column) of element e, advanced without divisions
+    const int dy = blockDim.x / W, dc = blockDim.x - dy * W;
     for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        const int y = e / W, c = e - y * W;
         double v = __longlong_as_double(0x7ff8000000000000LL);
+        float vf = __int_as_float(0x7fc00000);
         if (y < len) {
             const long long f = t - y;
             const T colT = f >= 0 ? A.cur_cols[f * W + c] : A.prev_cols[((R - 1) + f) * W + c];
-            const double col = (double)colT;
-            if (!finite_d(col)) v = __longlong_as_double(0x7ff8000000000000LL);
-            else if constexpr (sizeof(T) == 8) v = __ddiv_rn(__dsub_rn(col, lo), range);      // numpy's fp64 arithmetic
-            else v = (double)__fdiv_rn(__fsub_rn(colT, (float)lo), (float)range);              // float32 rows: float32 value
+            if constexpr (sizeof(T) == 8) {                           // numpy's fp64 arithmetic
+                if (finite_d(colT)) v = __ddiv_rn(__dsub_rn(colT, lo), range);
+                vf = (float)v;
+            } else {                                                  // float32 rows: float32 value
+                if (fabsf(colT) <= 3.402823466e38f) vf = __fdiv_rn(__fsub_rn(colT, lo_f), range_f);
+                v = (double)vf;
+            }
         }
-        if (A.norm) A.norm[base + e] = (float)v;
+        if (A.norm) A.norm[base + e] = vf;
         if (A.norm64) A.norm64[base + e] = v;
         if (A.plane_a) {
             uint8_t a, b;
@@ -141,6 +147,12 @@ __global__ void __launch_bounds__(256) display_render_kernel(const RenderArgs<T>
             quantise(v, A.kind, A.H, A.colours[min(31, R - (len - 1 - y))], a, b);
             A.plane_a[base + e] = a;
             if (A.plane_b) A.plane_b[base + e] = b;
+        }
+        y += dy;
+        c += dc;
+        if (c >= W) {
+            c -= W;
+            ++y;
         }
     }
 }

@@ -25,7 +25,9 @@ def test_bench_line_contract():
               "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
         assert k in j, k
     assert j["unit"] == "Msamples/s" and j["scaling"] == "weak" and j["vs_baseline"] is None
-    assert j["n_gpus"] == 1 and j["steps"] == 3 and j["gpu_launches"] == 9
+    assert j["n_gpus"] == 1 and j["steps"] == 3
+    # PSD + display render + (iq-correction coefficients, forcing, scan) kernels of the demodulator, every step
+    assert j["gpu_launches"] == 3 * 5
     assert "workload" in j["config"] and "model" not in j["config"]
     r = j["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
