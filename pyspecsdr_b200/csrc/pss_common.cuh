@@ -54,8 +54,8 @@ struct pss_ctx {
     void* d_aux = nullptr;  size_t d_aux_bytes = 0;
     void* d_aux2 = nullptr; size_t d_aux2_bytes = 0;
     // pipeline scratch (pss_pipeline.cu)
-    void* p_buf[12] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t p_bytes[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    void* p_buf[16] = {};
+    size_t p_bytes[16] = {};
     // demod plans keyed by (mode, fs, N)
     std::map<std::string, pss_demod_plan*> demod_plans;
     // display rings (pss_display.cu)

@@ -250,78 +250,97 @@ demod_force_kernel(const DecimDev D, const float2* __restrict__ iq, const int n_
 // ------------------------------------------------------------------------------------------------ kernel 1, fused
 // The same products with the discriminator computed where the tensor-core fragment needs it: lane
 // (r = lane / 4, c = lane % 4) of k-step ks owns window sample r*q + 4*ks + c of chunk r, which is exactly
-// the A-fragment element of mma.m8n8k4.  Each lane loads ONE IQ sample per k-step (a depth-PD register
-// pipeline keeps PD loads in flight), corrects it once, and takes the later neighbour from lane c+1 or,
-// for c == 3, from the next k-step's sample of lane (r, 0).  No shared-memory window, no warp barrier,
-// any q; shared memory holds the response table only.
-template <int SF, bool EDGE_CHECK, bool TAB_SMEM, int DIAG, int UNR>
+// the A-fragment element of mma.m8n8k4.  Each lane loads ONE IQ sample per k-step and chunk group (a depth-PD
+// register pipeline keeps the loads in flight), corrects it once, and takes the later neighbour from lane c+1
+// or, for c == 3, from the next k-step's sample of lane (r, 0).  No shared-memory window, no warp barrier,
+// any q; shared memory holds the response table only.  A warp works on U consecutive groups of 8 chunks at a
+// time and feeds every table fragment it loads to U tensor-core products: the kernel is bound by the
+// shared-memory / shuffle data path (ncu: 69 % of the LSU wavefront peak at U = 1), not by issue or the DMMA pipe.
+template <int SF, bool EDGE_CHECK, bool TAB_SMEM, int DIAG, int UNR, int U>
 __device__ __forceinline__ void force_unit_fused(const DecimDev& D, const float2* __restrict__ x, const int g0, const IqCorr kc,
                                                  const double* __restrict__ tab, const double* __restrict__ trow,
-                                                 double (&c0)[(SF + 8) / 8], double (&c1)[(SF + 8) / 8], double& racc,
-                                                 const int lane) {
+                                                 double (&c0)[U][(SF + 8) / 8], double (&c1)[U][(SF + 8) / 8],
+                                                 double (&racc)[U], const int lane) {
     constexpr bool WFM = SF == 16;
-    constexpr int NTD = (SF + 8) / 8, PD = 6;
+    constexpr int NTD = (SF + 8) / 8, PD = U == 1 ? 6 : 4;
     const int r = lane >> 2, c = lane & 3, KS = D.KS, N = D.N, L = D.N - 1;
-    const int e0 = r * D.q + c;
+    const int e0 = r * D.q + c, ustep = 8 * D.q;                      // group u starts 8 chunks further
     const float2* xp = x + g0 + e0;
-    auto load = [&](int ks) {
+    auto load = [&](int ks, int u) {
         bool ok = ks <= KS;
         if (EDGE_CHECK) {
-            const int gi = g0 + e0 + 4 * ks;
+            const int gi = g0 + u * ustep + e0 + 4 * ks;
             ok = ok && gi >= 0 && gi < N;
         }
         float2 v = make_float2(0.f, 0.f);
         if (DIAG == 3) return make_float2(1.f + ks, 0.5f * lane);                   // DIAG 3: timing without the IQ loads
-        if (ok) v = __ldg(xp + 4 * ks);
+        if (ok) v = __ldg(xp + u * ustep + 4 * ks);
         return v;
     };
-    float2 ring[PD];
-#pragma unroll
-    for (int i = 0; i < PD; ++i) ring[i] = load(i + 1);
     // iq_correction (signal_processing.py:55-71) up to its positive common factor 1 / (q_amp * cos_phi), which a
     // phase difference does not see: (I', Q') = (I / alpha, Q - sin_phi / alpha * I) -- two operations per sample
     auto correct = [&](const float2 v) { return make_float2(__fmul_rn(kc.inv_a, v.x), __fmaf_rn(kc.g, v.x, v.y)); };
-    float2 S0 = load(0);
-    if (WFM) S0 = correct(S0);
+    float2 ring[U][PD], S0[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int i = 0; i < PD; ++i) ring[u][i] = load(i + 1, u);
+        S0[u] = load(0, u);
+        if (WFM) S0[u] = correct(S0[u]);
+    }
     const double* bp = tab + lane;
     const double* tp = trow + c;
     const int src0 = lane & ~3;
-    double racc1 = 0.0;
+    double racc1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) racc1[u] = 0.0;
 #pragma unroll UNR
     for (int ks = 0; ks < KS; ++ks) {
-        float2 S1 = ring[0];
+        double av[U];
 #pragma unroll
-        for (int i = 0; i + 1 < PD; ++i) ring[i] = ring[i + 1];
-        ring[PD - 1] = load(ks + PD + 1);
-        if (WFM) S1 = correct(S1);
-        float2 a, n;
-        a.x = __shfl_down_sync(0xffffffffu, S0.x, 1);
-        a.y = __shfl_down_sync(0xffffffffu, S0.y, 1);
-        n.x = __shfl_sync(0xffffffffu, S1.x, src0);
-        n.y = __shfl_sync(0xffffffffu, S1.y, src0);
-        if (c == 3) a = n;
-        float d = DIAG == 2 ? a.x + S0.y : disc_core<WFM>(a, S0, D.scale);      // DIAG 2: timing without the discriminator math
-        if (EDGE_CHECK) {
-            const int g = g0 + e0 + 4 * ks;
-            if (g < 0 || g >= L) d = 0.f;
+        for (int u = 0; u < U; ++u) {
+            float2 S1 = ring[u][0];
+#pragma unroll
+            for (int i = 0; i + 1 < PD; ++i) ring[u][i] = ring[u][i + 1];
+            ring[u][PD - 1] = load(ks + PD + 1, u);
+            if (WFM) S1 = correct(S1);
+            float2 a, n;
+            a.x = __shfl_down_sync(0xffffffffu, S0[u].x, 1);
+            a.y = __shfl_down_sync(0xffffffffu, S0[u].y, 1);
+            n.x = __shfl_sync(0xffffffffu, S1.x, src0);
+            n.y = __shfl_sync(0xffffffffu, S1.y, src0);
+            if (c == 3) a = n;
+            float d = DIAG == 2 ? a.x + S0[u].y : disc_core<WFM>(a, S0[u], D.scale);   // DIAG 2: timing without the discriminator math
+            if (EDGE_CHECK) {
+                const int g = g0 + u * ustep + e0 + 4 * ks;
+                if (g < 0 || g >= L) d = 0.f;
+            }
+            av[u] = (double)d;
+            S0[u] = S1;
         }
-        const double av = (double)d;
 #pragma unroll
         for (int nt = 0; nt < NTD; ++nt) {
             double b;
             if (TAB_SMEM) b = bp[(ks * NTD + nt) * 32];
             else b = __ldg(bp + (ks * NTD + nt) * 32);
-            if (DIAG == 1) c0[nt] = fma(av, b, c0[nt]);                             // DIAG 1: timing without the tensor pipe
-            else dmma_m8n8k4(c0[nt], c1[nt], av, b);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (DIAG == 1) c0[u][nt] = fma(av[u], b, c0[u][nt]);                 // DIAG 1: timing without the tensor pipe
+                else dmma_m8n8k4(c0[u][nt], c1[u][nt], av[u], b);
+            }
         }
-        if (ks & 1) racc1 = fma(av, TAB_SMEM ? tp[4 * ks] : __ldg(tp + 4 * ks), racc1);
-        else racc = fma(av, TAB_SMEM ? tp[4 * ks] : __ldg(tp + 4 * ks), racc);
-        S0 = S1;
+        const double tr = TAB_SMEM ? tp[4 * ks] : __ldg(tp + 4 * ks);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (ks & 1) racc1[u] = fma(av[u], tr, racc1[u]);
+            else racc[u] = fma(av[u], tr, racc[u]);
+        }
     }
-    racc += racc1;
+#pragma unroll
+    for (int u = 0; u < U; ++u) racc[u] += racc1[u];
 }
 
-template <int SF, bool TAB_SMEM, int DIAG = 0, int UNR = 4, int MINB = 3>
+template <int SF, bool TAB_SMEM, int DIAG = 0, int UNR = 4, int MINB = 3, int U = 1>
 __global__ void __launch_bounds__(FORCE_THREADS, MINB)
 demod_force_fused_kernel(const DecimDev D, const float2* __restrict__ iq, const int n_frames, double* __restrict__ F,
                          const float4* __restrict__ corr) {
@@ -338,46 +357,47 @@ demod_force_fused_kernel(const DecimDev D, const float2* __restrict__ iq, const 
         __syncthreads();
     }
     const double* trow = tab + (size_t)D.KS * NTD * 32;               // [KS][4]: r-row taps
-    const int q = D.q, groups = D.groups, CS = D.CS;
-    const int n_units = n_frames * groups;
+    const int q = D.q, CS = D.CS;
+    const int sgroups = (D.groups + U - 1) / U;                       // super-groups of U * 8 chunks per block
+    const int n_units = n_frames * sgroups;
     const int wstride = gridDim.x * (FORCE_THREADS / 32);
     for (int unit = blockIdx.x * (FORCE_THREADS / 32) + warp; unit < n_units; unit += wstride) {
-        const int frame = unit / groups;
-        const int g = unit - frame * groups;
+        const int frame = unit / sgroups;
+        const int g = (unit - frame * sgroups) * U;
         const float2* x = iq + (long long)frame * D.N;
         IqCorr kc = {1.f, 1.f, 0.f, 1.f};
         if (WFM && D.iq_correct) {
             const float4 cf = __ldg(corr + frame);
             kc = {cf.x, cf.y, cf.z, cf.w};
         }
-        const int g0 = 8 * g * q + 1 - D.lead;                        // first discriminator index of the group
-        if (DIAG != 4 && unit + wstride < n_units) {
-            // pull the warp's NEXT window into L2 as whole 128-byte lines while this one is consumed 32 bytes
-            // per row and k-step (the next unit of a warp is wstride units ahead: another block, same group)
-            const int nu = unit + wstride, nfr = nu / groups, ng = nu - nfr * groups;
-            const char* nb = reinterpret_cast<const char*>(iq + (long long)nfr * D.N + max(8 * ng * q + 1 - D.lead, 0));
-            const int bytes = min((7 * q + 4 * D.KS + 4) * 8, (D.N - max(8 * ng * q + 1 - D.lead, 0)) * 8);
-            for (int o = lane * 128; o < bytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nb + o));
+        const int g0 = 8 * g * q + 1 - D.lead;                        // first discriminator index of the first group
+        double c0[U][NTD], c1[U][NTD], racc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            racc[u] = 0.0;
+#pragma unroll
+            for (int nt = 0; nt < NTD; ++nt) c0[u][nt] = c1[u][nt] = 0.0;
         }
-        double c0[NTD], c1[NTD], racc = 0.0;
-#pragma unroll
-        for (int nt = 0; nt < NTD; ++nt) c0[nt] = c1[nt] = 0.0;
-        if (g0 >= 0 && g0 + 7 * q + 4 * D.KS + 4 < D.N)
-            force_unit_fused<SF, false, TAB_SMEM, DIAG, UNR>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
+        if (g0 >= 0 && g0 + (8 * U - 1) * q + 4 * D.KS + 4 < D.N)
+            force_unit_fused<SF, false, TAB_SMEM, DIAG, UNR, U>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
         else
-            force_unit_fused<SF, true, TAB_SMEM, DIAG, UNR>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
-        racc += __shfl_xor_sync(0xffffffffu, racc, 1);
-        racc += __shfl_xor_sync(0xffffffffu, racc, 2);
-        const int c = 8 * g + (lane >> 2);                            // chunk index (body chunk j = c + 1)
-        if (c < D.n_body) {
-            double* col = F + (long long)frame * D.slot_doubles + c;
+            force_unit_fused<SF, true, TAB_SMEM, DIAG, UNR, U>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
 #pragma unroll
-            for (int nt = 0; nt < NTD; ++nt) {
-                const int row = nt * 8 + 2 * (lane & 3);
-                col[(long long)row * CS] = c0[nt];
-                col[(long long)(row + 1) * CS] = c1[nt];
+        for (int u = 0; u < U; ++u) {
+            double ra = racc[u];
+            ra += __shfl_xor_sync(0xffffffffu, ra, 1);
+            ra += __shfl_xor_sync(0xffffffffu, ra, 2);
+            const int c = 8 * (g + u) + (lane >> 2);                  // chunk index (body chunk j = c + 1)
+            if (c < D.n_body) {
+                double* col = F + (long long)frame * D.slot_doubles + c;
+#pragma unroll
+                for (int nt = 0; nt < NTD; ++nt) {
+                    const int row = nt * 8 + 2 * (lane & 3);
+                    col[(long long)row * CS] = c0[u][nt];
+                    col[(long long)(row + 1) * CS] = c1[u][nt];
+                }
+                if ((lane & 3) == 0) col[(long long)RROW * CS] = ra;
             }
-            if ((lane & 3) == 0) col[(long long)RROW * CS] = racc;
         }
     }
 }
@@ -793,11 +813,18 @@ static int launch_force(pss_ctx* ctx, pss_demod_plan* pl, const float2* iq, long
     if (g1 > per_sm * ctx->sm_count) g1 = per_sm * ctx->sm_count;
     const int tb = D.fused_tab_smem;
     static const int diag = getenv("PSS_DIAG") ? atoi(getenv("PSS_DIAG")) : 0;   // timing-only builds, wrong results
+    static const int var = getenv("PSS_FORCE_VARIANT") ? atoi(getenv("PSS_FORCE_VARIANT")) : 0;   // tuning experiments
     if (tb && diag) {
         auto k = diag == 1 ? demod_force_fused_kernel<SF, true, 1> : diag == 2 ? demod_force_fused_kernel<SF, true, 2>
                  : diag == 3 ? demod_force_fused_kernel<SF, true, 3> : demod_force_fused_kernel<SF, true, 4>;
         PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
         k<<<(unsigned)g1, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, F, corr);
+    } else if (tb && var) {
+        // 1: two groups per warp, 2 CTAs / SM;  2: two groups per warp, 3 CTAs / SM (80 registers)
+        auto k = var == 1 ? demod_force_fused_kernel<SF, true, 0, 3, 2, 2> : demod_force_fused_kernel<SF, true, 0, 3, 3, 2>;
+        PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
+        long long gv = (var == 1 ? 2LL : 3LL) * ctx->sm_count;
+        k<<<(unsigned)gv, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, F, corr);
     } else if (tb) {
         auto k = demod_force_fused_kernel<SF, true>;
         PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
@@ -825,14 +852,18 @@ int pss_decim_launch(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t 
                      const double* moments, int mom_fpb) {
     DecimDev& D = pl->dec;
     int rc;
-    // Sub-batches: the forcing scratch of a sub-batch stays in L2 (<= 40 MB) between the forcing kernel and
-    // the scan kernel, both on the context's stream.
+    // Sub-batches: the forcing scratch of a sub-batch stays in L2 (<= 56 MB, a whole number of scan-kernel waves:
+    // measured 0.88 / 0.79 / 0.76 / 0.72 / 0.73 ms per GiB NFM at 296 / 592 / 689 / 888 / 1184 blocks) between the
+    // forcing kernel and the scan kernel, both on the context's stream.
     // PSS_DEMOD_OVERLAP=1 (measured, not the default: 0.95 / 1.12 ms per GiB NFM / WFM against 0.75 / 0.86
     // serial): two half-size scratch buffers, the scan kernel of sub-batch k on a side stream beside the
     // forcing kernel of sub-batch k+1 at 2 CTAs / SM.
     const size_t slot_b = (size_t)D.slot_doubles * 8;
     static const bool want_overlap = getenv("PSS_DEMOD_OVERLAP") != nullptr;
-    long long sub = (long long)(((want_overlap ? 20u : 40u) << 20) / slot_b);
+    long long sub = (long long)(((want_overlap ? 20u : 56u) << 20) / slot_b);
+    if (!want_overlap && sub >= 3LL * ctx->sm_count) sub -= sub % (3LL * ctx->sm_count);   // whole waves of scan CTAs (3 / SM)
+    static const long long sub_env = getenv("PSS_DEMOD_SUB") ? atoll(getenv("PSS_DEMOD_SUB")) : 0;      // tuning
+    if (sub_env > 0) sub = sub_env;
     if (sub < 1) sub = 1;
     if (sub > n_frames) sub = n_frames;
     const bool overlap = want_overlap && n_frames > sub && !use_window_variant();

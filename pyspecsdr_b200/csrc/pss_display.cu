@@ -125,34 +125,48 @@ __global__ void __launch_bounds__(256) display_render_kernel(const RenderArgs<T>
     const float lo_f = (float)lo, range_f = (float)range;
     int y = threadIdx.x / W, c = threadIdx.x - y * W;                 // (row, column) of element e, advanced without divisions
     const int dy = blockDim.x / W, dc = blockDim.x - dy * W;
-    for (int e = threadIdx.x; e < total; e += blockDim.x) {
-        double v = __longlong_as_double(0x7ff8000000000000LL);
-        float vf = __int_as_float(0x7fc00000);
-        if (y < len) {
-            const long long f = t - y;
-            const T colT = f >= 0 ? A.cur_cols[f * W + c] : A.prev_cols[((R - 1) + f) * W + c];
-            if constexpr (sizeof(T) == 8) {                           // numpy's fp64 arithmetic
-                if (finite_d(colT)) v = __ddiv_rn(__dsub_rn(colT, lo), range);
-                vf = (float)v;
-            } else {                                                  // float32 rows: float32 value
-                if (fabsf(colT) <= 3.402823466e38f) vf = __fdiv_rn(__fsub_rn(colT, lo_f), range_f);
-                v = (double)vf;
+    constexpr int UN = 4;                                             // loads of UN elements in flight per thread
+    const T nanT = sizeof(T) == 8 ? (T)__longlong_as_double(0x7ff8000000000000LL) : (T)__int_as_float(0x7fc00000);
+    for (int e0 = threadIdx.x; e0 < total; e0 += UN * blockDim.x) {
+        T col[UN];
+        int yy[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            yy[u] = y;
+            col[u] = nanT;
+            if (e0 + u * (int)blockDim.x < total && y < len) {
+                const long long f = t - y;
+                col[u] = f >= 0 ? __ldg(A.cur_cols + f * W + c) : __ldg(A.prev_cols + ((R - 1) + f) * W + c);
+            }
+            y += dy;
+            c += dc;
+            if (c >= W) {
+                c -= W;
+                ++y;
             }
         }
-        if (A.norm) A.norm[base + e] = vf;
-        if (A.norm64) A.norm64[base + e] = v;
-        if (A.plane_a) {
-            uint8_t a, b;
-            // persistence trace i (oldest = 0) of a history of `len` rows: alpha = 0.7 ** (rows_max - i), i = len-1-y
-            quantise(v, A.kind, A.H, A.colours[min(31, R - (len - 1 - y))], a, b);
-            A.plane_a[base + e] = a;
-            if (A.plane_b) A.plane_b[base + e] = b;
-        }
-        y += dy;
-        c += dc;
-        if (c >= W) {
-            c -= W;
-            ++y;
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int e = e0 + u * (int)blockDim.x;
+            if (e >= total) break;
+            double v;
+            float vf;
+            if constexpr (sizeof(T) == 8) {                           // numpy's fp64 arithmetic
+                v = finite_d(col[u]) ? __ddiv_rn(__dsub_rn(col[u], lo), range) : __longlong_as_double(0x7ff8000000000000LL);
+                vf = (float)v;
+            } else {                                                  // float32 rows: float32 value
+                vf = fabsf(col[u]) <= 3.402823466e38f ? __fdiv_rn(__fsub_rn(col[u], lo_f), range_f) : __int_as_float(0x7fc00000);
+                v = (double)vf;
+            }
+            if (A.norm) A.norm[base + e] = vf;
+            if (A.norm64) A.norm64[base + e] = v;
+            if (A.plane_a) {
+                uint8_t a, b;
+                // persistence trace i (oldest = 0) of a history of `len` rows: alpha = 0.7 ** (rows_max - i), i = len-1-y
+                quantise(v, A.kind, A.H, A.colours[min(31, max(0, R - (len - 1 - yy[u])))], a, b);
+                A.plane_a[base + e] = a;
+                if (A.plane_b) A.plane_b[base + e] = b;
+            }
         }
     }
 }

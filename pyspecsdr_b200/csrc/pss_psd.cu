@@ -84,6 +84,238 @@ __device__ __forceinline__ void hist_pick(const unsigned* h, unsigned& rank, uns
 }
 
 
+// The main-loop epilogue on one dB row held in shared memory (pyspecsdr.py:2278-2283, 388-389, and the
+// W-column np.interp resample of the draw_* functions): 5-bin 'valid' mean, exact median - 10 dB clamp, row
+// statistics, stores.  Called by every thread of the frame's group of TPF = N/16 threads; `row` [N] raw dB
+// (fft-shifted), `srow` [N] and `hist` [1024] frame-local shared scratch; (rmin, rmax, rnan) = bounds / NaN flag
+// of the raw values this thread produced or loaded (together the threads cover the whole row).
+template <int N, int TPF>
+__device__ __forceinline__ void smooth_epilogue(const float* __restrict__ row, float* __restrict__ srow, unsigned* hist,
+                                                unsigned* us, unsigned* uf, float* cand, double* dscr, float* fscr,
+                                                const float rmin, const float rmax, const bool rnan, const int t,
+                                                const bool live, const long long frame, const PsdParams& p) {
+        // Thread t owns four groups of 4 consecutive bins, group q at 4*t + 4*TPF*q: float4 shared and
+        // global accesses with a 16-byte lane stride (conflict-free, fully coalesced).
+        constexpr int n = N - 4;
+        constexpr int CAP = TPF < 64 ? TPF : 64;
+        const int wf = t >> 5, lane = t & 31, nw = TPF / 32;
+        {   // bounds of the raw row (they bound every 5-bin mean), NaN flag; before the row barrier
+            const unsigned kmn = __reduce_min_sync(0xffffffffu, f2key(rmin));
+            const unsigned kmx = __reduce_max_sync(0xffffffffu, f2key(rmax));
+            if (lane == 0) {
+                atomicMin(&us[0], kmn);
+                atomicMax(&us[1], kmx);
+            }
+            if (__any_sync(0xffffffffu, rnan) && lane == 0) atomicOr(&us[6], 1u);
+        }
+        for (int b = t; b < 512; b += TPF) hist[b] = 0u;     // the exchange buffer is dead after the last pass
+        __syncthreads();                                     // B1: row complete, histograms clear, bounds known
+        float s[16];
+        unsigned b16[16];
+        bool gvalid[4];
+        {
+            const float lo = key2f(us[0]), hi = key2f(us[1]);
+            const float scale = hi > lo ? 65535.0f / (hi - lo) : 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i0 = 4 * t + 4 * TPF * q;
+                gvalid[q] = i0 < n;
+                const float4 a = *reinterpret_cast<const float4*>(row + i0);
+                const float4 c = i0 + 4 < N ? *reinterpret_cast<const float4*>(row + i0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float d[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float v = ((d[e] + d[e + 1]) + (d[e + 2] + d[e + 3]) + d[e + 4]) * 0.2f;
+                    s[4 * q + e] = v;
+                    // monotone 16-bit bucket over the occupied dB range (NaN and negatives convert to 0)
+                    b16[4 * q + e] = min(65535u, __float2uint_rz((v - lo) * scale));
+                }
+            }
+        }
+        // exact lower/upper median: two 8-bit histogram levels over the linear buckets, then the few
+        // elements of the selected bucket are ranked directly (flat rows fall back to a key radix select)
+        unsigned rank = (unsigned)((n - 1) / 2), d0, d1, m;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (gvalid[q]) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) atomicAdd(&hist[b16[4 * q + e] >> 8], 1u);
+            }
+        __syncthreads();                                     // B2
+        hist_pick(hist, rank, d0, m, lane);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (gvalid[q]) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if ((b16[4 * q + e] >> 8) == d0) atomicAdd(&hist[256 + (b16[4 * q + e] & 255u)], 1u);
+            }
+        __syncthreads();                                     // B3
+        hist_pick(hist + 256, rank, d1, m, lane);
+        const unsigned sel = (d0 << 8) | d1;
+        const bool flat = m > (unsigned)CAP;
+        {
+            const bool need_above = rank + 1u >= m;          // frame-uniform: upper median lies above the bucket
+            float fgt = INFINITY;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (gvalid[q]) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const unsigned b = b16[4 * q + e];
+                        if (b == sel && !flat) {
+                            const unsigned slot = atomicAdd(&us[2], 1u);
+                            if (slot < (unsigned)CAP) cand[slot] = s[4 * q + e];
+                        }
+                        if (need_above && b > sel) fgt = fminf(fgt, s[4 * q + e]);
+                    }
+                }
+            if (need_above) {
+                const unsigned kgt = __reduce_min_sync(0xffffffffu, f2key(fgt));
+                if (lane == 0) atomicMin(&us[3], kgt);
+            }
+        }
+        float v1, v2;
+        if (!__syncthreads_or(flat)) {                       // B4
+            if ((unsigned)t < m) {
+                const float c = cand[t];
+                unsigned rk = 0;
+                for (unsigned j = 0; j < m; ++j) {
+                    const float o = cand[j];
+                    rk += (o < c) || (o == c && j < (unsigned)t);
+                }
+                if (rk == rank) us[4] = __float_as_uint(c);
+                if (rk == rank + 1u) us[5] = __float_as_uint(c);
+            }
+            __syncthreads();                                 // B5
+            v1 = __uint_as_float(us[4]);
+            v2 = (n & 1) ? v1 : (rank + 1u < m ? __uint_as_float(us[5]) : key2f(us[3]));
+        } else {
+            // ---- rare path (a frame of this CTA has > CAP equal-bucket elements): 4 x 8-bit radix select
+            // on order-preserving keys normalised to the occupied key range; every frame of the CTA runs it
+            unsigned key[16];
+            unsigned kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+            for (int m2 = 0; m2 < 16; ++m2) {
+                key[m2] = f2key(s[m2]);
+                if (gvalid[m2 >> 2]) {
+                    kmin = min(kmin, key[m2]);
+                    kmax = max(kmax, key[m2]);
+                }
+            }
+            for (int b = t; b < 1024; b += TPF) hist[b] = 0u;
+            kmin = __reduce_min_sync(0xffffffffu, kmin);
+            kmax = __reduce_max_sync(0xffffffffu, kmax);
+            if (lane == 0) {
+                atomicMin(&uf[0], kmin);
+                atomicMax(&uf[1], kmax);
+            }
+            __syncthreads();
+            kmin = uf[0];
+            kmax = uf[1];
+            const int common = min(__clz((int)(kmin ^ kmax)), 31);
+#pragma unroll
+            for (int m2 = 0; m2 < 16; ++m2) key[m2] = (key[m2] - kmin) << common;
+            unsigned rk = (unsigned)((n - 1) / 2), prefix = 0u, dg, cnt;
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                const int shift = 24 - 8 * ps;
+                unsigned* h = hist + ps * 256;
+#pragma unroll
+                for (int m2 = 0; m2 < 16; ++m2) {
+                    const bool match = ps == 0 ? true : (key[m2] >> (shift + 8)) == prefix;
+                    if (gvalid[m2 >> 2] && match) atomicAdd(&h[(key[m2] >> shift) & 255u], 1u);
+                }
+                __syncthreads();
+                hist_pick(h, rk, dg, cnt, lane);
+                prefix = (prefix << 8) | dg;
+            }
+            const unsigned key1n = prefix;                   // normalised key of the lower median
+            unsigned cnt_le = 0, min_gt = 0xffffffffu;
+#pragma unroll
+            for (int m2 = 0; m2 < 16; ++m2) {
+                if (gvalid[m2 >> 2]) {
+                    cnt_le += key[m2] <= key1n;
+                    if (key[m2] > key1n) min_gt = min(min_gt, key[m2]);
+                }
+            }
+            cnt_le = __reduce_add_sync(0xffffffffu, cnt_le);
+            min_gt = __reduce_min_sync(0xffffffffu, min_gt);
+            if (lane == 0) {
+                atomicAdd(&uf[2], cnt_le);
+                atomicMin(&uf[3], min_gt);
+            }
+            __syncthreads();
+            const unsigned key2n = ((n & 1) || uf[2] > (unsigned)(n / 2)) ? key1n : uf[3];
+            v1 = key2f((key1n >> common) + kmin);
+            v2 = key2f((key2n >> common) + kmin);
+        }
+        float thr = (float)(0.5 * ((double)v1 + (double)v2) - 10.0);
+        const bool any_nan = us[6] != 0u;
+        if (any_nan) thr = __int_as_float(0x7fc00000);       // np.median propagates NaN
+        // clamp, row statistics, store
+        float mx = -INFINITY, mn = INFINITY, fsum = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float v = s[4 * q + e];
+                if (v < thr) v = thr;
+                s[4 * q + e] = v;
+                if (gvalid[q]) {
+                    mx = fmaxf(mx, v);
+                    mn = fminf(mn, v);
+                    fsum += v;
+                }
+            }
+            const int i0 = 4 * t + 4 * TPF * q;
+            const float4 o = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
+            *reinterpret_cast<float4*>(srow + i0) = o;
+            if (live && p.db && gvalid[q]) *reinterpret_cast<float4*>(p.db + frame * n + i0) = o;
+        }
+        mx = warp_max(mx);
+        mn = warp_min(mn);
+        const double dsum = warp_sum((double)fsum);
+        if (lane == 0) {
+            fscr[wf] = mx;
+            fscr[16 + wf] = mn;
+            dscr[wf] = dsum;
+        }
+        __syncthreads();                                     // B6: clamped row + warp partials visible
+        if (live && p.stats && t == 0) {
+            float a = fscr[0], b = fscr[16];
+            double sm = dscr[0];
+            for (int w = 1; w < nw; ++w) {
+                a = fmaxf(a, fscr[w]);
+                b = fminf(b, fscr[16 + w]);
+                sm += dscr[w];
+            }
+            const float nanv = __int_as_float(0x7fc00000);
+            float4 st;
+            st.x = any_nan ? nanv : a;                    // np.max
+            st.y = any_nan ? nanv : (float)(sm / n);      // np.mean
+            st.z = b;                                     // finite min
+            st.w = a;                                     // finite max
+            reinterpret_cast<float4*>(p.stats)[frame] = st;
+        }
+        if (live && p.cols) {
+            const int W = p.W;
+            const double step = p.col_step;                  // (n - 1) / (W - 1), 0 for W == 1
+            for (int c = t; c < W; c += TPF) {
+                const double x = (c == W - 1 && W > 1) ? (double)(n - 1) : c * step;
+                const int j = (int)x;
+                float o;
+                if (j >= n - 1) {
+                    o = srow[n - 1];
+                } else {
+                    const double y0 = srow[j], y1 = srow[j + 1];
+                    o = (float)((y1 - y0) * (x - (double)j) + y0);
+                }
+                p.cols[frame * W + c] = o;
+            }
+        }
+}
+
 // One Stockham pass P >= 1 (shared -> registers -> shared, or -> `out` on the last pass).
 struct CtaBarrier {
     __device__ __forceinline__ void operator()() const { __syncthreads(); }
@@ -211,7 +443,7 @@ psd_kernel(const PsdParams p) {
             for (int r = 0; r < 16; ++r) {
                 const int idx = t + r * TPF;
                 const float2 s = live ? __ldg(src + idx) : make_float2(0.f, 0.f);
-                if constexpr (EPI == EPI_SMOOTH && N >= 512) {
+                if constexpr (EPI != EPI_SCAN && N >= 512) {
                     mii = fmaf(s.x, s.x, mii);
                     mqq = fmaf(s.y, s.y, mqq);
                     miq = fmaf(s.x, s.y, miq);
@@ -223,7 +455,7 @@ psd_kernel(const PsdParams p) {
                     v[r] = {(T)s.x, (T)s.y};
                 }
             }
-            if constexpr (EPI == EPI_SMOOTH && N >= 512) {
+            if constexpr (EPI != EPI_SCAN && N >= 512) {
                 if (p.moments) {          // frame moments: float partials per warp, fp64 across the frame
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
@@ -245,7 +477,7 @@ psd_kernel(const PsdParams p) {
         for (int q = 0; q < 16; ++q) buf[fft_swz(base + fft_perm<16>(q))] = v[q];
     }
     __syncthreads();
-    if constexpr (EPI == EPI_SMOOTH && N >= 512 && LOG2N1 == 0) {
+    if constexpr (EPI != EPI_SCAN && N >= 512 && LOG2N1 == 0) {
         if (p.moments && live && t == 0) {
             double a = 0.0, b = 0.0, c = 0.0;
             for (int w = 0; w < TPF / 32; ++w) {
@@ -337,233 +569,51 @@ psd_kernel(const PsdParams p) {
         }
     }
 
-    if constexpr (EPI == EPI_SMOOTH) {
-        // Thread t owns four groups of 4 consecutive bins, group q at 4*t + 4*TPF*q: float4 shared and
-        // global accesses with a 16-byte lane stride (conflict-free, fully coalesced).
-        constexpr int n = N - 4;
-        constexpr int CAP = C::CAP;
-        const int wf = t >> 5, lane = t & 31, nw = TPF / 32;
-        unsigned* us = us_s[f];
-        float* cand = cand_s[f];
-        {   // bounds of the raw row (they bound every 5-bin mean), NaN flag; before the row barrier
-            const unsigned kmn = __reduce_min_sync(0xffffffffu, f2key(rmin));
-            const unsigned kmx = __reduce_max_sync(0xffffffffu, f2key(rmax));
-            if (lane == 0) {
-                atomicMin(&us[0], kmn);
-                atomicMax(&us[1], kmx);
-            }
-            if (__any_sync(0xffffffffu, rnan) && lane == 0) atomicOr(&us[6], 1u);
-        }
-        for (int b = t; b < 512; b += TPF) hist[b] = 0u;     // the exchange buffer is dead after the last pass
-        __syncthreads();                                     // B1: row complete, histograms clear, bounds known
-        float s[16];
-        unsigned b16[16];
-        bool gvalid[4];
-        {
-            const float lo = key2f(us[0]), hi = key2f(us[1]);
-            const float scale = hi > lo ? 65535.0f / (hi - lo) : 0.f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i0 = 4 * t + 4 * TPF * q;
-                gvalid[q] = i0 < n;
-                const float4 a = *reinterpret_cast<const float4*>(row + i0);
-                const float4 c = i0 + 4 < N ? *reinterpret_cast<const float4*>(row + i0 + 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                const float d[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const float v = ((d[e] + d[e + 1]) + (d[e + 2] + d[e + 3]) + d[e + 4]) * 0.2f;
-                    s[4 * q + e] = v;
-                    // monotone 16-bit bucket over the occupied dB range (NaN and negatives convert to 0)
-                    b16[4 * q + e] = min(65535u, __float2uint_rz((v - lo) * scale));
-                }
-            }
-        }
-        // exact lower/upper median: two 8-bit histogram levels over the linear buckets, then the few
-        // elements of the selected bucket are ranked directly (flat rows fall back to a key radix select)
-        unsigned rank = (unsigned)((n - 1) / 2), d0, d1, m;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (gvalid[q]) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) atomicAdd(&hist[b16[4 * q + e] >> 8], 1u);
-            }
-        __syncthreads();                                     // B2
-        hist_pick(hist, rank, d0, m, lane);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (gvalid[q]) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if ((b16[4 * q + e] >> 8) == d0) atomicAdd(&hist[256 + (b16[4 * q + e] & 255u)], 1u);
-            }
-        __syncthreads();                                     // B3
-        hist_pick(hist + 256, rank, d1, m, lane);
-        const unsigned sel = (d0 << 8) | d1;
-        const bool flat = m > (unsigned)CAP;
-        {
-            const bool need_above = rank + 1u >= m;          // frame-uniform: upper median lies above the bucket
-            float fgt = INFINITY;
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (gvalid[q]) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const unsigned b = b16[4 * q + e];
-                        if (b == sel && !flat) {
-                            const unsigned slot = atomicAdd(&us[2], 1u);
-                            if (slot < (unsigned)CAP) cand[slot] = s[4 * q + e];
-                        }
-                        if (need_above && b > sel) fgt = fminf(fgt, s[4 * q + e]);
-                    }
-                }
-            if (need_above) {
-                const unsigned kgt = __reduce_min_sync(0xffffffffu, f2key(fgt));
-                if (lane == 0) atomicMin(&us[3], kgt);
-            }
-        }
-        float v1, v2;
-        if (!__syncthreads_or(flat)) {                       // B4
-            if ((unsigned)t < m) {
-                const float c = cand[t];
-                unsigned rk = 0;
-                for (unsigned j = 0; j < m; ++j) {
-                    const float o = cand[j];
-                    rk += (o < c) || (o == c && j < (unsigned)t);
-                }
-                if (rk == rank) us[4] = __float_as_uint(c);
-                if (rk == rank + 1u) us[5] = __float_as_uint(c);
-            }
-            __syncthreads();                                 // B5
-            v1 = __uint_as_float(us[4]);
-            v2 = (n & 1) ? v1 : (rank + 1u < m ? __uint_as_float(us[5]) : key2f(us[3]));
-        } else {
-            // ---- rare path (a frame of this CTA has > CAP equal-bucket elements): 4 x 8-bit radix select
-            // on order-preserving keys normalised to the occupied key range; every frame of the CTA runs it
-            unsigned* uf = uf_s[f];
-            unsigned key[16];
-            unsigned kmin = 0xffffffffu, kmax = 0u;
-#pragma unroll
-            for (int m2 = 0; m2 < 16; ++m2) {
-                key[m2] = f2key(s[m2]);
-                if (gvalid[m2 >> 2]) {
-                    kmin = min(kmin, key[m2]);
-                    kmax = max(kmax, key[m2]);
-                }
-            }
-            for (int b = t; b < 1024; b += TPF) hist[b] = 0u;
-            kmin = __reduce_min_sync(0xffffffffu, kmin);
-            kmax = __reduce_max_sync(0xffffffffu, kmax);
-            if (lane == 0) {
-                atomicMin(&uf[0], kmin);
-                atomicMax(&uf[1], kmax);
-            }
-            __syncthreads();
-            kmin = uf[0];
-            kmax = uf[1];
-            const int common = min(__clz((int)(kmin ^ kmax)), 31);
-#pragma unroll
-            for (int m2 = 0; m2 < 16; ++m2) key[m2] = (key[m2] - kmin) << common;
-            unsigned rk = (unsigned)((n - 1) / 2), prefix = 0u, dg, cnt;
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                const int shift = 24 - 8 * ps;
-                unsigned* h = hist + ps * 256;
-#pragma unroll
-                for (int m2 = 0; m2 < 16; ++m2) {
-                    const bool match = ps == 0 ? true : (key[m2] >> (shift + 8)) == prefix;
-                    if (gvalid[m2 >> 2] && match) atomicAdd(&h[(key[m2] >> shift) & 255u], 1u);
-                }
-                __syncthreads();
-                hist_pick(h, rk, dg, cnt, lane);
-                prefix = (prefix << 8) | dg;
-            }
-            const unsigned key1n = prefix;                   // normalised key of the lower median
-            unsigned cnt_le = 0, min_gt = 0xffffffffu;
-#pragma unroll
-            for (int m2 = 0; m2 < 16; ++m2) {
-                if (gvalid[m2 >> 2]) {
-                    cnt_le += key[m2] <= key1n;
-                    if (key[m2] > key1n) min_gt = min(min_gt, key[m2]);
-                }
-            }
-            cnt_le = __reduce_add_sync(0xffffffffu, cnt_le);
-            min_gt = __reduce_min_sync(0xffffffffu, min_gt);
-            if (lane == 0) {
-                atomicAdd(&uf[2], cnt_le);
-                atomicMin(&uf[3], min_gt);
-            }
-            __syncthreads();
-            const unsigned key2n = ((n & 1) || uf[2] > (unsigned)(n / 2)) ? key1n : uf[3];
-            v1 = key2f((key1n >> common) + kmin);
-            v2 = key2f((key2n >> common) + kmin);
-        }
-        float thr = (float)(0.5 * ((double)v1 + (double)v2) - 10.0);
-        const bool any_nan = us[6] != 0u;
-        if (any_nan) thr = __int_as_float(0x7fc00000);       // np.median propagates NaN
-        // clamp, row statistics, store
-        float mx = -INFINITY, mn = INFINITY, fsum = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float v = s[4 * q + e];
-                if (v < thr) v = thr;
-                s[4 * q + e] = v;
-                if (gvalid[q]) {
-                    mx = fmaxf(mx, v);
-                    mn = fminf(mn, v);
-                    fsum += v;
-                }
-            }
-            const int i0 = 4 * t + 4 * TPF * q;
-            const float4 o = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
-            *reinterpret_cast<float4*>(srow + i0) = o;
-            if (live && p.db && gvalid[q]) *reinterpret_cast<float4*>(p.db + frame * n + i0) = o;
-        }
-        mx = warp_max(mx);
-        mn = warp_min(mn);
-        const double dsum = warp_sum((double)fsum);
-        if (lane == 0) {
-            fscr[wf] = mx;
-            fscr[16 + wf] = mn;
-            dscr[wf] = dsum;
-        }
-        __syncthreads();                                     // B6: clamped row + warp partials visible
-        if (live && p.stats && t == 0) {
-            float a = fscr[0], b = fscr[16];
-            double sm = dscr[0];
-            for (int w = 1; w < nw; ++w) {
-                a = fmaxf(a, fscr[w]);
-                b = fminf(b, fscr[16 + w]);
-                sm += dscr[w];
-            }
-            const float nanv = __int_as_float(0x7fc00000);
-            float4 st;
-            st.x = any_nan ? nanv : a;                    // np.max
-            st.y = any_nan ? nanv : (float)(sm / n);      // np.mean
-            st.z = b;                                     // finite min
-            st.w = a;                                     // finite max
-            reinterpret_cast<float4*>(p.stats)[frame] = st;
-        }
-        if (live && p.cols) {
-            const int W = p.W;
-            const double step = p.col_step;                  // (n - 1) / (W - 1), 0 for W == 1
-            for (int c = t; c < W; c += TPF) {
-                const double x = (c == W - 1 && W > 1) ? (double)(n - 1) : c * step;
-                const int j = (int)x;
-                float o;
-                if (j >= n - 1) {
-                    o = srow[n - 1];
-                } else {
-                    const double y0 = srow[j], y1 = srow[j + 1];
-                    o = (float)((y1 - y0) * (x - (double)j) + y0);
-                }
-                p.cols[frame * W + c] = o;
-            }
-        }
-    }
+    if constexpr (EPI == EPI_SMOOTH)
+        smooth_epilogue<N, TPF>(row, srow, hist, us_s[f], uf_s[f], cand_s[f], dscr, fscr, rmin, rmax, rnan, t, live, frame, p);
 }
 
+
+// The same epilogue as a kernel of its own, one CTA of N/16 threads per raw dB row (N = 4096, 8192).  The
+// fused kernel keeps a 64 KB fp64 exchange buffer per frame, so only 2 of its CTAs fit an SM and the
+// epilogue's barriers and shared atomics are latency the SM cannot hide; here a CTA needs 36 KB and
+// ~64 registers, 4 are resident, and the rows come out of L2 (the caller runs transform and epilogue
+// over L2-sized chunks of frames, so the raw rows never reach DRAM).
+struct PsdEpiParams {
+    const float* raw;     // [n_frames][N] raw dB rows
+    long long n_frames;
+    PsdParams out;        // db / cols / W / stats / col_step
+};
+
+template <int LOG2N>
+__global__ void __launch_bounds__((1 << LOG2N) / 16, LOG2N == 12 ? 4 : 2)
+psd_epilogue_kernel(const PsdEpiParams q) {
+    constexpr int N = 1 << LOG2N, TPF = N / 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* row = reinterpret_cast<float*>(smem_raw);
+    float* srow = row + N;
+    unsigned* hist = reinterpret_cast<unsigned*>(srow + N);          // [1024]
+    __shared__ unsigned us[16], uf[8];
+    __shared__ float cand[64];
+    __shared__ double dscr[16];
+    __shared__ float fscr[32];
+    const int t = threadIdx.x;
+    const long long frame = blockIdx.x;
+    if (t < 16) us[t] = (t == 0 || t == 3) ? 0xffffffffu : 0u;
+    if (t < 8) uf[t] = (t == 0 || t == 3) ? 0xffffffffu : 0u;
+    const float4* src = reinterpret_cast<const float4*>(q.raw + frame * N);
+    float rmin = INFINITY, rmax = -INFINITY;
+    bool rnan = false;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        const float4 v = __ldcs(src + t + g * TPF);
+        reinterpret_cast<float4*>(row)[t + g * TPF] = v;
+        rmin = fminf(fminf(rmin, v.x), fminf(fminf(v.y, v.z), v.w));
+        rmax = fmaxf(fmaxf(rmax, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
+        rnan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
+    }
+    smooth_epilogue<N, TPF>(row, srow, hist, us, uf, cand, dscr, fscr, rmin, rmax, rnan, t, true, frame, q.out);
+}
 
 // ---------------------------------------------------------------------------------- large transforms
 // N = N1 * N2 (N1 = 4, 8, 16; N2 = 4096 or 8192), four-step FFT:
@@ -1385,7 +1435,8 @@ extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_f
         return PSS_ERR_ARG;
     if (precision != PSS_PREC_FP64 && precision != PSS_PREC_FP32) return PSS_ERR_ARG;
     if (epilogue == PSS_EPI_RAW && !out->db) return PSS_ERR_ARG;
-    if (epilogue == PSS_EPI_RAW && (out->cols || out->stats || out->moments)) return PSS_ERR_UNSUPPORTED;
+    if (epilogue == PSS_EPI_RAW && (out->cols || out->stats)) return PSS_ERR_UNSUPPORTED;
+    if (epilogue == PSS_EPI_RAW && out->moments && (N < 512 || N > 8192)) return PSS_ERR_UNSUPPORTED;
     if (out->moments && N > 65536) return PSS_ERR_UNSUPPORTED;
     if (out->cols && out->W < 1) return PSS_ERR_ARG;
     const int log2n = ilog2_exact(N);
@@ -1411,7 +1462,49 @@ extern "C" int pss_psd_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_f
     p.moments = out->moments;
     if (fp32) return launch_by_n<float, EPI_RAW>(ctx, log2n, p);
     if (epilogue == PSS_EPI_RAW) return launch_by_n<double, EPI_RAW>(ctx, log2n, p);
-    return launch_by_n<double, EPI_SMOOTH>(ctx, log2n, p);
+    // PSS_PSD_SPLIT=1 (measured, not the default: 4096-point 1.11 / 1.03 / 0.98 ms per GiB at 32 / 64 / 128 MB chunks
+    // against 0.93 fused): transform and epilogue as two kernels over chunks of frames whose raw dB rows stay in
+    // L2, the epilogue at 4 CTAs / SM instead of 2.  The epilogue is bound by its ~64 instructions per bin, not by
+    // the barrier latency the extra occupancy hides, so the fused kernel stays the product path.
+    static const bool split = getenv("PSS_PSD_SPLIT") != nullptr;
+    if (!split || log2n < 12) return launch_by_n<double, EPI_SMOOTH>(ctx, log2n, p);
+    static const long long chunk_mb = getenv("PSS_PSD_CHUNK_MB") ? atoll(getenv("PSS_PSD_CHUNK_MB")) : 128;
+    long long chunk = (chunk_mb << 20) / ((long long)N * 4);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_frames) chunk = n_frames;
+    if ((rc = pss_reserve(ctx, &ctx->p_buf[12], &ctx->p_bytes[12], (size_t)chunk * N * 4))) return rc;
+    float* raw = (float*)ctx->p_buf[12];
+    const size_t n_out = (size_t)N - 4;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk) {
+        const long long nf = n_frames - f0 < chunk ? n_frames - f0 : chunk;
+        PsdParams pr = p;
+        pr.iq = p.iq + f0 * N;
+        pr.n_frames = nf;
+        pr.db = raw;
+        pr.cols = nullptr;
+        pr.stats = nullptr;
+        pr.moments = p.moments ? p.moments + f0 * 4 : nullptr;
+        if ((rc = launch_by_n<double, EPI_RAW>(ctx, log2n, pr))) return rc;
+        PsdEpiParams q{};
+        q.raw = raw;
+        q.n_frames = nf;
+        q.out = PsdParams{};
+        q.out.db = p.db ? p.db + f0 * n_out : nullptr;
+        q.out.cols = p.cols ? p.cols + f0 * p.W : nullptr;
+        q.out.W = p.W;
+        q.out.stats = p.stats ? p.stats + f0 * 4 : nullptr;
+        if (p.W > 1) q.out.col_step = (double)(N - 4 - 1) / (double)(p.W - 1);
+        const size_t sm = (size_t)N * 8 + 4096;
+        if (log2n == 12) {
+            PSS_CUDA(ctx, cudaFuncSetAttribute(psd_epilogue_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            psd_epilogue_kernel<12><<<(unsigned)nf, 256, sm, ctx->stream>>>(q);
+        } else {
+            PSS_CUDA(ctx, cudaFuncSetAttribute(psd_epilogue_kernel<13>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+            psd_epilogue_kernel<13><<<(unsigned)nf, 512, sm, ctx->stream>>>(q);
+        }
+        PSS_LAUNCH_CHECK(ctx);
+    }
+    return PSS_OK;
 }
 
 extern "C" int pss_scan_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_t n_steps, int use_abs,
