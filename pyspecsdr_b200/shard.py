@@ -43,6 +43,19 @@ def gather_sweep(peak, count, rows=None, n_steps: Optional[int] = None, group=No
         n_steps = int(t.item())
     sizes = shard_sizes(n_steps, world)
     m = max(sizes)
+    if min(sizes) == m:
+        # equal shares (1000 steps over 1 / 2 / 4 / 8 ranks): every rank's records land at their final place in
+        # one all_gather_into_tensor each - the (peak, count) pairs travel together as 8-byte records
+        rec = torch.empty(m, 2, dtype=torch.int32, device=peak.device)
+        rec[:, 0] = peak.view(torch.int32)
+        rec[:, 1] = count
+        allrec = torch.empty(n_steps, 2, dtype=torch.int32, device=peak.device)
+        dist.all_gather_into_tensor(allrec, rec, group=group)
+        allrows = None
+        if rows is not None:
+            allrows = torch.empty((n_steps,) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+            dist.all_gather_into_tensor(allrows, rows.contiguous(), group=group)
+        return allrec[:, 0].contiguous().view(torch.float32), allrec[:, 1].contiguous(), allrows
 
     def ag(x):
         pad = torch.zeros((m,) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)

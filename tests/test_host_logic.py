@@ -154,9 +154,10 @@ def _gloo_worker(rank, world, port, n_steps, N, q):
     dist.destroy_process_group()
 
 
-def test_scanner_gather_world2_gloo_bitwise_equals_single_rank():
+@pytest.mark.parametrize("n_steps", [11, 12])      # ragged shares (padded all_gather) and equal shares (one all_gather_into_tensor)
+def test_scanner_gather_world2_gloo_bitwise_equals_single_rank(n_steps):
     import torch.multiprocessing as mp
-    n_steps, N, world = 11, 512, 2
+    N, world = 512, 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + os.getpid() % 2000
