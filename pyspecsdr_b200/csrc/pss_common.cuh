@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <map>
+#include <set>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -64,6 +65,7 @@ struct pss_ctx {
     std::map<int, pss_large_tables> large_tables;
     void* hann_periodic = nullptr;
     pss_pipe_streams pipe;
+    std::set<const void*> configured;    // kernels whose dynamic shared-memory limit was raised on this device
 };
 
 int pss_fail_cuda(pss_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);

@@ -929,10 +929,28 @@ struct PsdLargeParams {
     double* moments;               // [n_frames][4] sum I^2, Q^2, IQ per frame (by-product for the WFM demod), or null
 };
 
-template <int LOG2N, int EPI>
+// Cluster helpers (thread-block clusters, sm_90+): rank of this CTA in its cluster and a full cluster barrier
+// whose release / acquire makes the global-memory rows written before it visible to the other CTAs.
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// CL = CTAs per frame.  One CTA per frame (CL = 1) keeps grid x N x 16 bytes of fp64 rows alive: 38 MB at 16384
+// points, 76 MB at 32768 - more than the L2 holds beside the input stream, so half of the scratch went to DRAM
+// and back (ncu, round 1: 2.5x the algorithmic traffic).  A cluster of CL CTAs on CL SMs shares ONE frame: every
+// CTA transforms 1/CL of the columns and, after a cluster barrier, 1/CL of the rows, so only grid / CL frames
+// are in flight (38 MB again at 32768 with CL = 2, at 65536 with CL = 4) and the rows stay in L2.  With the
+// epilogue the cluster takes CL frames at a time and every CTA finishes one of them.
+template <int LOG2N, int EPI, int CL>
 __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams p) {
     constexpr int N = 1 << LOG2N, LOG2N1 = LOG2N - 12, N1 = 1 << LOG2N1, N2 = 4096, n = N - 4;
     constexpr bool SROW_SMEM = (size_t)N * 4 <= 2 * fft_padded(N2) * sizeof(cx<double>);
+    static_assert((N2 / 512) % CL == 0 && (N1 / 2) % CL == 0, "columns and row pairs must split evenly over the cluster");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned hist[512];
     __shared__ unsigned us[8], ub[2];
@@ -941,25 +959,35 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
     __shared__ float fmx_s[16], fmn_s[16];
     __shared__ double mom_s[16][3];
     const int tid = threadIdx.x, g = tid >> 8, t = tid & 255, lane = tid & 31, warp = tid >> 5;
+    const int rank = CL > 1 ? (int)cluster_ctarank() : 0;
+    const long long cid = blockIdx.x / CL, ncl = gridDim.x / CL;
     cx<double>* buf = reinterpret_cast<cx<double>*>(smem_raw) + (size_t)g * fft_padded(N2);
     const HalfBarrier hbar{1 + g};
     cx<double> wpre[2];
     wpre[0] = p.tw[t & 15];                       // pass 1: ns = 16, offset 0
     wpre[1] = p.tw[16 + t];                       // pass 2: ns = 256, offset (256-16)/15 = 16
-    cx<double>* Y = p.Y + (size_t)blockIdx.x * N;
-    float* raw = EPI == EPI_SMOOTH ? p.rawdb + (size_t)blockIdx.x * N : nullptr;
+    cx<double>* Y = p.Y + (size_t)cid * N;
+    float* rawbase = EPI == EPI_SMOOTH ? p.rawdb + (size_t)cid * CL * N : nullptr;
     const unsigned long long keep = l2_evict_last_policy();
 
-    for (long long frame = blockIdx.x; frame < p.n_frames; frame += gridDim.x) {
-        // ---- stage A: column DFTs
-        if constexpr (EPI == EPI_SMOOTH) {
-            if (tid < 8) us[tid] = tid == 3 ? 0xffffffffu : 0u;
-            if (tid < 2) ub[tid] = tid == 0 ? 0xffffffffu : 0u;      // raw-row bounds (keys)
+    // with the epilogue the cluster works on groups of CL consecutive frames, otherwise frame by frame
+    constexpr int FPG = EPI == EPI_SMOOTH ? CL : 1;
+    for (long long grp = cid; grp * FPG < p.n_frames; grp += ncl) {
+      for (int j = 0; j < FPG; ++j) {
+        const long long frame = grp * FPG + j;
+        if (frame >= p.n_frames) {                // ragged last group: keep the barrier count uniform
+            if (CL > 1) {
+                cluster_barrier();
+                cluster_barrier();
+            }
+            continue;
         }
+        float* raw = EPI == EPI_SMOOTH ? rawbase + (size_t)j * N : nullptr;
+        // ---- stage A: column DFTs of this CTA's share of the columns
         const float2* src = p.iq + frame * N;
         float mii = 0.f, mqq = 0.f, miq = 0.f;
 #pragma unroll(N1 == 4 ? 4 : N1 == 8 ? 2 : 1)
-        for (int c = 0; c < N2 / 512; ++c) {
+        for (int c = rank * (N2 / 512 / CL); c < (rank + 1) * (N2 / 512 / CL); ++c) {
             const int n2 = tid + 512 * c;
             cx<double> v[N1];
 #pragma unroll
@@ -1012,20 +1040,27 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
                     c += mom_s[w][2];
                 }
                 double* m = p.moments + frame * 4;
-                m[0] = a; m[1] = b; m[2] = c; m[3] = 0.0;
+                if (CL == 1) {
+                    m[0] = a; m[1] = b; m[2] = c; m[3] = 0.0;
+                } else {                      // every CTA of the cluster adds its columns' share (zeroed by the host)
+                    atomicAdd(m, a);
+                    atomicAdd(m + 1, b);
+                    atomicAdd(m + 2, c);
+                }
             }
         }
         if constexpr (LOG2N == 14) {
             // pull the next frame of this CTA into L2 while the row transforms keep the fp64 pipe busy
             // (measured: -4 % at 16384 points; at 32768+ the scratch already fills the L2 and it hurts)
-            const long long nf = frame + gridDim.x;
+            const long long nf = frame + gridDim.x;                       // (CL == 1 at 16384 points)
             if (nf < p.n_frames) {
                 const char* nx = reinterpret_cast<const char*>(p.iq + nf * N);
                 for (int l = tid; l < N * 8 / 128; l += 512) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + (size_t)l * 128));
             }
         }
+        if (CL > 1) cluster_barrier();            // every column of the frame is in the scratch
         // ---- stage B: row transforms, two rows at a time
-        for (int pair = 0; pair < N1 / 2; ++pair) {
+        for (int pair = rank * (N1 / 2 / CL); pair < (rank + 1) * (N1 / 2 / CL); ++pair) {
             const int k1 = 2 * pair + g;
             {
                 const double2* rowY = reinterpret_cast<const double2*>(Y + k1 * N2);
@@ -1050,8 +1085,18 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
             stockham_pass<12, 1, double, true>(buf, &wpre[0], t, [](int, cx<double>) {}, hbar);
             stockham_pass<12, 2, double, true>(buf, &wpre[1], t, emit, hbar);
         }
-        __syncthreads();
-        if constexpr (EPI == EPI_SMOOTH) {
+        if (CL > 1) cluster_barrier();            // every row is transformed: the scratch may be overwritten
+        else __syncthreads();
+      }
+      // ---- epilogue: CTA `rank` finishes frame grp * CL + rank
+      if constexpr (EPI == EPI_SMOOTH) {
+        const long long frame = grp * CL + rank;
+        if (frame < p.n_frames) {
+            float* raw = rawbase + (size_t)rank * N;
+            if (tid < 8) us[tid] = tid == 3 ? 0xffffffffu : 0u;
+            if (tid < 2) ub[tid] = tid == 0 ? 0xffffffffu : 0u;      // raw-row bounds (keys)
+            __syncthreads();
+        {
             float* srow = SROW_SMEM ? reinterpret_cast<float*>(smem_raw) : p.srow2 + (size_t)blockIdx.x * N;
             bool has_nan = false;
             float rlo = INFINITY, rhi = -INFINITY;
@@ -1148,6 +1193,9 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
             }
             __syncthreads();          // srow (shared) is the next frame's exchange buffer
         }
+        }
+        if (CL > 1) cluster_barrier();            // the raw rows of this group are consumed
+      }
     }
 }
 
@@ -1187,11 +1235,8 @@ template <int LOG2N, typename T, int EPI>
 static int launch_one(pss_ctx* ctx, const PsdParams& p) {
     using C = PsdCfg<LOG2N, T>;
     auto kern = psd_kernel<LOG2N, T, EPI>;
-    static bool configured[16] = {};
-    if (!configured[ctx->device & 15]) {
+    if (ctx->configured.insert((const void*)kern).second)      // once per context (the attribute is per device)
         PSS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-        configured[ctx->device & 15] = true;
-    }
     const long long grid = (p.n_frames + C::FPC - 1) / C::FPC;
     PsdParams q = p;
     q.ahead = ctx->sm_count * ((EPI == EPI_SMOOTH && C::MINB == 2) ? PSS_SMOOTH_MINB : C::MINB);
@@ -1258,18 +1303,36 @@ static int launch_stage_b(pss_ctx* ctx, const PsdParams& p) {
 }
 
 
-template <int LOG2N, int EPI>
+template <int LOG2N, int EPI, int CL>
 static int launch_large_fused(pss_ctx* ctx, const PsdLargeParams& p, unsigned grid) {
-    auto kern = psd_large_kernel<LOG2N, EPI>;
+    auto kern = psd_large_kernel<LOG2N, EPI, CL>;
     constexpr int SMEM = 2 * fft_padded(4096) * (int)sizeof(cx<double>);
-    static bool configured[16] = {};
-    if (!configured[ctx->device & 15]) {
-        PSS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-        configured[ctx->device & 15] = true;
+    PSS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    if (CL == 1) {
+        kern<<<grid, 512, SMEM, ctx->stream>>>(p);
+    } else {
+        // thread-block cluster of CL CTAs per frame (cudaLaunchKernelEx, cluster dimension attribute)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid, 1, 1);
+        cfg.blockDim = dim3(512, 1, 1);
+        cfg.dynamicSmemBytes = SMEM;
+        cfg.stream = ctx->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CL;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        PSS_CUDA(ctx, cudaLaunchKernelEx(&cfg, kern, p));
     }
-    kern<<<grid, 512, SMEM, ctx->stream>>>(p);
     PSS_LAUNCH_CHECK(ctx);
     return PSS_OK;
+}
+
+template <int LOG2N, int CL>
+static int launch_large_epi(pss_ctx* ctx, const PsdLargeParams& p, unsigned grid, bool smooth) {
+    return smooth ? launch_large_fused<LOG2N, EPI_SMOOTH, CL>(ctx, p, grid) : launch_large_fused<LOG2N, EPI_RAW, CL>(ctx, p, grid);
 }
 
 static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames, int window, int epilogue,
@@ -1320,8 +1383,21 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
     if (log2n <= 16 && !big) {
         // fused persistent kernel: per-CTA scratch only (grid * N * 16 bytes of fp64 rows + the raw dB row)
         const bool smooth = epilogue == PSS_EPI_SMOOTH_CLAMP;
-        const unsigned grid = (unsigned)(n_frames < ctx->sm_count ? n_frames : ctx->sm_count);
-        if ((rc = pss_reserve(ctx, &ctx->p_buf[7], &ctx->p_bytes[7], (size_t)grid * N * 16))) return rc;
+        // CTAs per frame.  PSS_LARGE_CL=2|4 runs a thread-block cluster per frame (32768 / 65536 points), which
+        // halves / quarters the frames in flight so that their fp64 scratch (grid / CL x N x 16 bytes) fits the L2
+        // again.  Measured on B200 (ms per GiB, raw / smoothing): 32768 points 1.41 / 2.02 at CL = 1, 1.64 / 2.16 at
+        // CL = 2; 65536 points 1.49 / 2.26 at CL = 1, 1.72 / 2.81 at CL = 2, 3.23 / 4.61 at CL = 4 - every CTA's
+        // phases are latency-bound (column loads, L2 row loads), so half the work per phase does not take half
+        // the time and the cluster barriers add their own.  One CTA per frame stays the default.
+        static const int cl_env = getenv("PSS_LARGE_CL") ? atoi(getenv("PSS_LARGE_CL")) : 0;
+        int CL = 1;
+        if (cl_env == 2 || cl_env == 4) CL = cl_env;
+        if (log2n == 14 && CL > 2) CL = 2;               // 4 column passes / 2 row pairs bound the split
+        if (log2n == 15 && CL > 4) CL = 4;
+        unsigned grid = (unsigned)(ctx->sm_count - ctx->sm_count % CL);
+        const long long groups = smooth ? (n_frames + CL - 1) / CL : n_frames;       // units of cluster work
+        if ((long long)grid / CL > groups) grid = (unsigned)(groups * CL);
+        if ((rc = pss_reserve(ctx, &ctx->p_buf[7], &ctx->p_bytes[7], (size_t)grid / CL * N * 16))) return rc;
         PsdLargeParams lp{};
         lp.iq = reinterpret_cast<const float2*>(iq);
         lp.window = window == PSS_WINDOW_NONE ? nullptr : (const double*)lt.window[window];
@@ -1341,10 +1417,14 @@ static int psd_large(pss_ctx* ctx, const float* iq, int log2n, int64_t n_frames,
                 if ((rc = pss_reserve(ctx, &ctx->p_buf[8], &ctx->p_bytes[8], (size_t)grid * N * 4))) return rc;
                 lp.srow2 = (float*)ctx->p_buf[8];
             }
+            if (CL > 1 && lp.moments) PSS_CUDA(ctx, cudaMemsetAsync(lp.moments, 0, (size_t)n_frames * 32, ctx->stream));
         }
-        if (log2n == 14) return smooth ? launch_large_fused<14, EPI_SMOOTH>(ctx, lp, grid) : launch_large_fused<14, EPI_RAW>(ctx, lp, grid);
-        if (log2n == 15) return smooth ? launch_large_fused<15, EPI_SMOOTH>(ctx, lp, grid) : launch_large_fused<15, EPI_RAW>(ctx, lp, grid);
-        return smooth ? launch_large_fused<16, EPI_SMOOTH>(ctx, lp, grid) : launch_large_fused<16, EPI_RAW>(ctx, lp, grid);
+        if (log2n == 14) return CL == 1 ? launch_large_epi<14, 1>(ctx, lp, grid, smooth) : launch_large_epi<14, 2>(ctx, lp, grid, smooth);
+        if (log2n == 15)
+            return CL == 1 ? launch_large_epi<15, 1>(ctx, lp, grid, smooth)
+                           : CL == 2 ? launch_large_epi<15, 2>(ctx, lp, grid, smooth) : launch_large_epi<15, 4>(ctx, lp, grid, smooth);
+        return CL == 1 ? launch_large_epi<16, 1>(ctx, lp, grid, smooth)
+                       : CL == 2 ? launch_large_epi<16, 2>(ctx, lp, grid, smooth) : launch_large_epi<16, 4>(ctx, lp, grid, smooth);
     }
     // 131072 points: three launches per L2-sized sub-batch.
     // scratch: fp64 rows of a sub-batch (kept <= 64 MB so it lives in L2) and, with an epilogue, the raw rows
@@ -1741,11 +1821,8 @@ extern "C" int pss_classify_c64_dev(pss_ctx* ctx, const float* iq, int N, int64_
     if ((rc = pss_reserve(ctx, &ctx->p_buf[8], &ctx->p_bytes[8], (size_t)n_blocks * 1024 * 8))) return rc;
     double* acc = (double*)ctx->p_buf[8];
     PSS_CUDA(ctx, cudaMemsetAsync(acc, 0, (size_t)n_blocks * 1024 * 8, ctx->stream));
-    static bool configured[16] = {};
-    if (!configured[ctx->device & 15]) {
+    if (ctx->configured.insert((const void*)welch_kernel).second)
         PSS_CUDA(ctx, cudaFuncSetAttribute(welch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
-        configured[ctx->device & 15] = true;
-    }
     welch_kernel<<<(unsigned)((total + 3) / 4), 256, 65536, ctx->stream>>>(
         reinterpret_cast<const float2*>(iq), N, n_seg, total, (const double*)hann, (const cx<double>*)tab->twiddle, acc);
     PSS_LAUNCH_CHECK(ctx);

@@ -28,4 +28,21 @@ ctx.iq_correct(blk[0])
 ctx.to_int16(np.zeros((100, 2), np.float32))
 res = ctx.psd(blk.reshape(-1, 4096), epilogue=True, W=200, want_stats=True)
 ctx.display_render(res["cols"], res["stats"], rows_max=30)
+# round 2: stateful display streams (fp64 host rows and float32 device-layout rows), the pipeline with a carried
+# ring and planes, exact int16 / spectrum paths, the scan kernel with its scratch in global memory (long block)
+rows = res["db"].astype(np.float64)
+for sid, (kind, R, H) in enumerate((("waterfall", 30, 0), ("gradient", 30, 0), ("persistence", 10, 36), ("surface", 1, 0))):
+    ctx.display_open(sid, kind, W=120, rows_max=R, H=H)
+    ctx.display_accumulate(sid, rows[:7])
+    ctx.display_accumulate(sid, rows[7:9])
+    ctx.display_close(sid)
+ctx.display_open(9, "waterfall", W=200, rows_max=30)
+ctx.pipeline(blk, 2.4e6, "WFM", n_fft=4096, W=200, rows_max=30, display_stream=9, want_planes=True)
+ctx.pipeline(blk[:1], 2.4e6, "NFM", n_fft=4096, W=200, rows_max=30, display_stream=9, want_planes=True)
+ctx.display_close(9)
+ctx.spectrum_normalise(rows[:3], 113)
+ctx.to_int16(np.linspace(-1, 1, 1001))
+ctx.demod(blk, 2.4e6, "WFM", iq_correct=False)
+ctx.demod(np.stack([synth.make("wbfm", 262144, seed=2)]), 250e3, "WFM")      # 23828 chunks: scratch stays in global memory
+ctx.demod(np.stack([synth.make("wbfm", 65536, seed=3)]), 20e6, "NFM")       # q = 907: table read from global memory
 print("sanitize workload done, launches", ctx.launches)
