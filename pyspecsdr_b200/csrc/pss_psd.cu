@@ -973,16 +973,19 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
     // with the epilogue the cluster works on groups of CL consecutive frames, otherwise frame by frame
     constexpr int FPG = EPI == EPI_SMOOTH ? CL : 1;
     for (long long grp = cid; grp * FPG < p.n_frames; grp += ncl) {
+#pragma unroll 1
       for (int j = 0; j < FPG; ++j) {
-        const long long frame = grp * FPG + j;
-        if (frame >= p.n_frames) {                // ragged last group: keep the barrier count uniform
-            if (CL > 1) {
-                cluster_barrier();
-                cluster_barrier();
-            }
+        const long long frame = FPG == 1 ? grp : grp * FPG + j;
+        if (FPG > 1 && frame >= p.n_frames) {     // ragged last group: keep the barrier count uniform
+            cluster_barrier();
+            cluster_barrier();
             continue;
         }
-        float* raw = EPI == EPI_SMOOTH ? rawbase + (size_t)j * N : nullptr;
+        float* raw = EPI == EPI_SMOOTH ? (FPG == 1 ? rawbase : rawbase + (size_t)j * N) : nullptr;
+        if constexpr (EPI == EPI_SMOOTH && CL == 1) {    // one CTA per frame: reset the median scratch ahead of the barriers below
+            if (tid < 8) us[tid] = tid == 3 ? 0xffffffffu : 0u;
+            if (tid < 2) ub[tid] = tid == 0 ? 0xffffffffu : 0u;      // raw-row bounds (keys)
+        }
         // ---- stage A: column DFTs of this CTA's share of the columns
         const float2* src = p.iq + frame * N;
         float mii = 0.f, mqq = 0.f, miq = 0.f;
@@ -1090,12 +1093,14 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
       }
       // ---- epilogue: CTA `rank` finishes frame grp * CL + rank
       if constexpr (EPI == EPI_SMOOTH) {
-        const long long frame = grp * CL + rank;
-        if (frame < p.n_frames) {
-            float* raw = rawbase + (size_t)rank * N;
-            if (tid < 8) us[tid] = tid == 3 ? 0xffffffffu : 0u;
-            if (tid < 2) ub[tid] = tid == 0 ? 0xffffffffu : 0u;      // raw-row bounds (keys)
-            __syncthreads();
+        const long long frame = CL == 1 ? grp : grp * CL + rank;
+        if (CL == 1 || frame < p.n_frames) {
+            float* raw = CL == 1 ? rawbase : rawbase + (size_t)rank * N;
+            if (CL > 1) {
+                if (tid < 8) us[tid] = tid == 3 ? 0xffffffffu : 0u;
+                if (tid < 2) ub[tid] = tid == 0 ? 0xffffffffu : 0u;  // raw-row bounds (keys)
+                __syncthreads();
+            }
         {
             float* srow = SROW_SMEM ? reinterpret_cast<float*>(smem_raw) : p.srow2 + (size_t)blockIdx.x * N;
             bool has_nan = false;
