@@ -674,28 +674,42 @@ def main():
         if not pinned:                                        # torch does not recognise the mapping: use its own
             hsrc = torch.empty(hsrc.numel(), dtype=torch.float32, pin_memory=True)
         dst = torch.empty(hsrc.numel(), device=dev, dtype=torch.float32)
-        cs = torch.cuda.Stream(device=dev)
-        with torch.cuda.stream(cs):
-            dst.copy_(hsrc, non_blocking=True)
+        back_d = torch.empty(d2h // 4, device=dev, dtype=torch.float32)           # the pipeline's D2H volume
+        back_h = torch.empty(d2h // 4, dtype=torch.float32, pin_memory=True)
+        cs, cs2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def probe(duplex):
+            with torch.cuda.stream(cs):
+                dst.copy_(hsrc, non_blocking=True)
             barrier()
             c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             c0.record(cs)
             for _ in range(args.e2e_steps):
-                dst.copy_(hsrc, non_blocking=True)
+                with torch.cuda.stream(cs):
+                    dst.copy_(hsrc, non_blocking=True)
+                if duplex:
+                    with torch.cuda.stream(cs2):
+                        back_h.copy_(back_d, non_blocking=True)
+            cs.wait_stream(cs2)
             c1.record(cs)
             barrier()
-            cms = c0.elapsed_time(c1) / args.e2e_steps
-        tc = torch.tensor([cms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
-        cms = float(tc.item())
+            ms = c0.elapsed_time(c1) / args.e2e_steps
+            tcp = torch.tensor([ms], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tcp, op=dist.ReduceOp.MAX)
+            return float(tcp.item())
+
+        cms, dms = probe(False), probe(True)
         ceil_msps = world * nb_e * N_BLOCK / cms / 1e3
+        dup_msps = world * nb_e * N_BLOCK / dms / 1e3
         ceiling = {"h2d_ceiling_gbs_per_gpu": h2d / cms / 1e6, "h2d_ceiling_gbs_total": world * h2d / cms / 1e6,
                    "h2d_ceiling_msamples_per_s": ceil_msps, "e2e_frac_of_ceiling": e2e["value"] / ceil_msps,
+                   "duplex_ceiling_msamples_per_s": dup_msps, "e2e_frac_of_duplex_ceiling": e2e["value"] / dup_msps,
                    "same_buffer": pinned,
                    "how": "cudaMemcpyAsync (torch copy_, non_blocking) of the pipeline's own pinned input buffer, all "
-                          "ranks concurrently, CUDA events, max over ranks"}
-        del dst
+                          "ranks concurrently, CUDA events, max over ranks; 'duplex' = the same with the pipeline's "
+                          "device-to-host volume copied the other way at the same time"}
+        del dst, back_d, back_h
     except Exception as ex:                                   # never fail the bench over the probe
         ceiling = {"error": f"{type(ex).__name__}: {ex}"}
     e2e.update(ceiling)
