@@ -84,7 +84,8 @@ struct RenderArgs {
     int colours[32];       // persistence: colour pair of the trace that is k-th newest in a history of full length
 };
 
-template <typename T>
+// PLANES = false: the lean instantiation for callers that only want the normalised values (the bench step).
+template <typename T, bool PLANES>
 __global__ void __launch_bounds__(256) display_render_kernel(const RenderArgs<T> A) {
     const long long r = blockIdx.x;
     const long long t = A.first + r * A.step;          // newest frame of this render
@@ -92,21 +93,35 @@ __global__ void __launch_bounds__(256) display_render_kernel(const RenderArgs<T>
     const int R = A.rows_max, W = A.W;
     const long long avail = t + 1 + A.n_prev;
     const int len = (int)(avail < R ? avail : R);      // rows in the history at this render
-    // stack range over the history rows (each row's finite min/max came with the row)
-    double lo = INFINITY, hi = -INFINITY;
-    for (int y = 0; y < len; ++y) {
-        const long long f = t - y;
-        double a, b;
-        if (f >= 0) {
-            a = (double)A.cur_mm[f * A.mm_stride + A.mm_off];
-            b = (double)A.cur_mm[f * A.mm_stride + A.mm_off + 1];
-        } else {
-            a = (double)A.prev_mm[((R - 1) + f) * 2];
-            b = (double)A.prev_mm[((R - 1) + f) * 2 + 1];
+    // stack range over the history rows (each row's finite min/max came with the row): lane y of the first warp
+    // takes row y, a warp reduction, one broadcast through shared memory (rows_max <= 31)
+    __shared__ double s_lohi[2];
+    if (threadIdx.x < 32) {
+        const int y = threadIdx.x;
+        T a = (T)INFINITY, b = (T)-INFINITY;              // rows without a finite value carry (+inf, -inf)
+        if (y < len) {
+            const long long f = t - y;
+            if (f >= 0) {
+                a = A.cur_mm[f * A.mm_stride + A.mm_off];
+                b = A.cur_mm[f * A.mm_stride + A.mm_off + 1];
+            } else {
+                a = A.prev_mm[((R - 1) + f) * 2];
+                b = A.prev_mm[((R - 1) + f) * 2 + 1];
+            }
         }
-        lo = fmin(lo, a);                               // rows without a finite value carry (+inf, -inf)
-        hi = fmax(hi, b);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const T oa = __shfl_xor_sync(0xffffffffu, a, o), ob = __shfl_xor_sync(0xffffffffu, b, o);
+            a = oa < a ? oa : a;                            // fmin / fmax semantics for the finite values stored here
+            b = ob > b ? ob : b;
+        }
+        if (threadIdx.x == 0) {
+            s_lohi[0] = (double)a;
+            s_lohi[1] = (double)b;
+        }
     }
+    __syncthreads();
+    const double lo = s_lohi[0], hi = s_lohi[1];
     double range = __dsub_rn(hi, lo);
     if (A.guard && range == 0.0) range = 1.0;
     if (threadIdx.x == 0) {
@@ -121,51 +136,91 @@ __global__ void __launch_bounds__(256) display_render_kernel(const RenderArgs<T>
         if (A.n_rows) A.n_rows[r] = len;
     }
     const long long base = r * (long long)R * W;
-    const int total = R * W;
     const float lo_f = (float)lo, range_f = (float)range;
-    int y = threadIdx.x / W, c = threadIdx.x - y * W;                 // (row, column) of element e, advanced without divisions
-    const int dy = blockDim.x / W, dc = blockDim.x - dy * W;
-    constexpr int UN = 4;                                             // loads of UN elements in flight per thread
-    const T nanT = sizeof(T) == 8 ? (T)__longlong_as_double(0x7ff8000000000000LL) : (T)__int_as_float(0x7fc00000);
-    for (int e0 = threadIdx.x; e0 < total; e0 += UN * blockDim.x) {
-        T col[UN];
-        int yy[UN];
+    if constexpr (!PLANES && sizeof(T) == 4) {
+        // float32 rows, values only (the pipeline / bench step): four columns per thread, 16-byte loads and stores
+        const bool vec = A.norm && (W & 3) == 0 &&
+                         ((((uintptr_t)A.cur_cols | (uintptr_t)A.prev_cols | (uintptr_t)A.norm) & 15) == 0);
+        if (vec) {
+            constexpr int UN = 3;
+            const int W4 = W >> 2, items = R * W4, nt = blockDim.x;
+            const float4* cur4 = reinterpret_cast<const float4*>(A.cur_cols);
+            const float4* prev4 = reinterpret_cast<const float4*>(A.prev_cols);
+            float4* out4 = reinterpret_cast<float4*>(A.norm + base);
+            const float qnan = __int_as_float(0x7fc00000);
+            const int dy = nt / W4, dc = nt - dy * W4;
+            int y = (int)threadIdx.x / W4, c = (int)threadIdx.x - y * W4;
+            for (int i0 = threadIdx.x; i0 < items; i0 += UN * nt) {
+                float4 v[UN];
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            yy[u] = y;
-            col[u] = nanT;
-            if (e0 + u * (int)blockDim.x < total && y < len) {
-                const long long f = t - y;
-                col[u] = f >= 0 ? __ldg(A.cur_cols + f * W + c) : __ldg(A.prev_cols + ((R - 1) + f) * W + c);
+                for (int u = 0; u < UN; ++u) {
+                    v[u] = make_float4(qnan, qnan, qnan, qnan);
+                    if (i0 + u * nt < items && y < len) {
+                        const long long f = t - y;
+                        const float4* src = f >= 0 ? cur4 + f * W4 : prev4 + ((R - 1) + f) * W4;
+                        v[u] = __ldg(src + c);
+                    }
+                    c += dc;
+                    y += dy;
+                    if (c >= W4) {
+                        c -= W4;
+                        ++y;
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    if (i0 + u * nt >= items) break;
+                    float4 o;
+                    o.x = fabsf(v[u].x) <= 3.402823466e38f ? __fdiv_rn(__fsub_rn(v[u].x, lo_f), range_f) : qnan;
+                    o.y = fabsf(v[u].y) <= 3.402823466e38f ? __fdiv_rn(__fsub_rn(v[u].y, lo_f), range_f) : qnan;
+                    o.z = fabsf(v[u].z) <= 3.402823466e38f ? __fdiv_rn(__fsub_rn(v[u].z, lo_f), range_f) : qnan;
+                    o.w = fabsf(v[u].w) <= 3.402823466e38f ? __fdiv_rn(__fsub_rn(v[u].w, lo_f), range_f) : qnan;
+                    out4[i0 + u * nt] = o;
+                }
             }
-            y += dy;
-            c += dc;
-            if (c >= W) {
-                c -= W;
-                ++y;
-            }
+            return;
         }
+    }
+    // thread = column, loop over the history rows (UN rows in flight): no index arithmetic per element
+    constexpr int UN = 5;
+    const T nanT = sizeof(T) == 8 ? (T)__longlong_as_double(0x7ff8000000000000LL) : (T)__int_as_float(0x7fc00000);
+    for (int c = threadIdx.x; c < W; c += blockDim.x) {
+        for (int y0 = 0; y0 < R; y0 += UN) {
+            T col[UN];
 #pragma unroll
-        for (int u = 0; u < UN; ++u) {
-            const int e = e0 + u * (int)blockDim.x;
-            if (e >= total) break;
-            double v;
-            float vf;
-            if constexpr (sizeof(T) == 8) {                           // numpy's fp64 arithmetic
-                v = finite_d(col[u]) ? __ddiv_rn(__dsub_rn(col[u], lo), range) : __longlong_as_double(0x7ff8000000000000LL);
-                vf = (float)v;
-            } else {                                                  // float32 rows: float32 value
-                vf = fabsf(col[u]) <= 3.402823466e38f ? __fdiv_rn(__fsub_rn(col[u], lo_f), range_f) : __int_as_float(0x7fc00000);
-                v = (double)vf;
+            for (int u = 0; u < UN; ++u) {
+                const int y = y0 + u;
+                col[u] = nanT;
+                if (y < len) {
+                    const long long f = t - y;
+                    col[u] = f >= 0 ? __ldg(A.cur_cols + f * W + c) : __ldg(A.prev_cols + ((R - 1) + f) * W + c);
+                }
             }
-            if (A.norm) A.norm[base + e] = vf;
-            if (A.norm64) A.norm64[base + e] = v;
-            if (A.plane_a) {
-                uint8_t a, b;
-                // persistence trace i (oldest = 0) of a history of `len` rows: alpha = 0.7 ** (rows_max - i), i = len-1-y
-                quantise(v, A.kind, A.H, A.colours[min(31, max(0, R - (len - 1 - yy[u])))], a, b);
-                A.plane_a[base + e] = a;
-                if (A.plane_b) A.plane_b[base + e] = b;
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int y = y0 + u;
+                if (y >= R) break;
+                const long long e = base + (long long)y * W + c;
+                double v;
+                float vf;
+                if constexpr (sizeof(T) == 8) {                       // numpy's fp64 arithmetic
+                    v = finite_d(col[u]) ? __ddiv_rn(__dsub_rn(col[u], lo), range) : __longlong_as_double(0x7ff8000000000000LL);
+                    vf = (float)v;
+                } else {                                              // float32 rows: float32 value
+                    vf = fabsf(col[u]) <= 3.402823466e38f ? __fdiv_rn(__fsub_rn(col[u], lo_f), range_f) : __int_as_float(0x7fc00000);
+                    v = (double)vf;
+                }
+                if (A.norm) A.norm[e] = vf;
+                if constexpr (PLANES || sizeof(T) == 8) {
+                    if (A.norm64) A.norm64[e] = v;
+                }
+                if constexpr (PLANES) if (A.plane_a) {
+                    uint8_t pa, pb;
+                    // persistence trace i (oldest = 0) of a history of `len` rows: alpha = 0.7 ** (rows_max - i), i = len-1-y
+                    quantise(v, A.kind, A.H, A.colours[min(31, max(0, R - (len - 1 - y)))], pa, pb);
+                    A.plane_a[e] = pa;
+                    if (A.plane_b) A.plane_b[e] = pb;
+                }
             }
         }
     }
@@ -474,7 +529,8 @@ static void persistence_colours(int rows_max, int* out) {
 template <typename T>
 static int run_render(pss_ctx* ctx, DisplayRing* ring, RenderArgs<T>& A, int64_t n_renders, bool carry) {
     if (n_renders > 0) {
-        display_render_kernel<T><<<(unsigned)n_renders, 256, 0, ctx->stream>>>(A);
+        if (A.plane_a || A.norm64) display_render_kernel<T, true><<<(unsigned)n_renders, 256, 0, ctx->stream>>>(A);
+        else display_render_kernel<T, false><<<(unsigned)n_renders, 256, 0, ctx->stream>>>(A);
         PSS_LAUNCH_CHECK(ctx);
     }
     if (carry && ring && ring->rows_max > 1) {

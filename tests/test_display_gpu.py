@@ -36,6 +36,21 @@ def test_waterfall_history_vs_oracle(ctx):
         assert np.all(np.isnan(norm[s, len(hist):]))
 
 
+@pytest.mark.parametrize("W,rows_max", [(200, 30), (113, 30), (66, 7), (4, 2), (1028, 31)])
+def test_render_widths_vs_oracle(ctx, W, rows_max):
+    """Both forms of the values-only render (16-byte path for W % 4 == 0, scalar otherwise) against the oracle,
+    with NaN padding for the rows the history does not hold yet."""
+    x, ref_rows = make_rows(rows_max + 3, 2048)
+    res = ctx.psd(x, epilogue=True, W=W, want_stats=True, want_db=False)
+    norm, mm = ctx.display_render(res["cols"], res["stats"], rows_max=rows_max)
+    hist = []
+    for s, r in enumerate(ref_rows):
+        want, (lo, hi), _, _ = O.waterfall_accumulate(hist, r, W, max_rows=rows_max)
+        assert np.max(np.abs(norm[s, :len(hist)] - want)) <= 1e-5
+        assert np.all(np.isnan(norm[s, len(hist):]))
+        assert abs(mm[s, 0] - lo) <= 1e-4 and abs(mm[s, 1] - hi) <= 1e-4
+
+
 def test_persistence_history_vs_oracle(ctx):
     x, ref_rows = make_rows(14)
     W, H = 112, 36
