@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpss.so")
+# PSS_LIB: another build of the same library (a compile-time variant under measurement), never a fallback
+LIB_PATH = os.environ.get("PSS_LIB") or os.path.join(_HERE, "libpss.so")
 
 
 class PssError(RuntimeError):

@@ -15,8 +15,11 @@
 #include "pss_fft.cuh"
 
 enum { EPI_RAW = 0, EPI_SMOOTH = 1, EPI_SCAN = 2 };
-#ifndef PSS_SMOOTH_MINB
-#define PSS_SMOOTH_MINB 2
+// CTAs per SM the smoothing variant's 64 KB configurations are compiled for (-DPSS_SMOOTH_MINB=n overrides)
+#ifdef PSS_SMOOTH_MINB
+constexpr int pss_smooth_minb(int) { return PSS_SMOOTH_MINB; }
+#else
+constexpr int pss_smooth_minb(int log2n) { return log2n <= 10 ? 3 : 2; }
 #endif
 
 struct PsdParams {
@@ -84,38 +87,103 @@ __device__ __forceinline__ void hist_pick(const unsigned* h, unsigned& rank, uns
 }
 
 
+// The same for a BINS-bin histogram (512 or 1024), run by ONE warp: stage 1 picks the segment of BINS/32
+// consecutive bins (lane L sums segment L, reading it in an order rotated by L so that the 32 lanes hit 32
+// banks), stage 2 the bin inside it (one bin per lane).
+template <int BINS>
+__device__ __forceinline__ void hist_pick_wide(const unsigned* h, unsigned& rank, unsigned& digit, unsigned& count,
+                                               const int lane) {
+    constexpr int SEG = BINS / 32;
+    const unsigned* seg = h + SEG * lane;
+    const int rot = SEG == 32 ? lane : (lane >> 1);
+    unsigned sum = 0;
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) sum += seg[(j + rot) & (SEG - 1)];
+    unsigned incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    const unsigned hit = __ballot_sync(0xffffffffu, incl > rank);
+    const int L = hit ? __ffs(hit) - 1 : 31;
+    const unsigned r = rank - __shfl_sync(0xffffffffu, incl - sum, L);
+    const unsigned c = lane < SEG ? h[SEG * L + lane] : 0u;
+    unsigned inc2 = c;
+#pragma unroll
+    for (int o = 1; o < SEG; o <<= 1) {
+        const unsigned up = __shfl_up_sync(0xffffffffu, inc2, o);
+        if (lane >= o) inc2 += up;
+    }
+    const unsigned hit2 = __ballot_sync(0xffffffffu, lane < SEG && inc2 > r);
+    const int l2 = hit2 ? __ffs(hit2) - 1 : SEG - 1;
+    digit = (unsigned)(SEG * L + l2);
+    count = __shfl_sync(0xffffffffu, c, l2);
+    rank = r - __shfl_sync(0xffffffffu, inc2 - c, l2);
+}
+
+
 // The main-loop epilogue on one dB row held in shared memory (pyspecsdr.py:2278-2283, 388-389, and the
 // W-column np.interp resample of the draw_* functions): 5-bin 'valid' mean, exact median - 10 dB clamp, row
 // statistics, stores.  Called by every thread of the frame's group of TPF = N/16 threads; `row` [N] raw dB
-// (fft-shifted), `srow` [N] and `hist` [1024] frame-local shared scratch; (rmin, rmax, rnan) = bounds / NaN flag
-// of the raw values this thread produced or loaded (together the threads cover the whole row).
+// (fft-shifted), `srow` [N] and `hist` [1024] frame-local shared scratch; (rsum, rsq, rnan) = sum, sum of squares and NaN
+// flag of the raw values this thread produced or loaded (together the threads cover the whole row).
 template <int N, int TPF>
 __device__ __forceinline__ void smooth_epilogue(const float* __restrict__ row, float* __restrict__ srow, unsigned* hist,
                                                 unsigned* us, unsigned* uf, float* cand, double* dscr, float* fscr,
-                                                const float rmin, const float rmax, const bool rnan, const int t,
+                                                const float rsum, const float rsq, const bool rnan, const int t,
                                                 const bool live, const long long frame, const PsdParams& p) {
         // Thread t owns four groups of 4 consecutive bins, group q at 4*t + 4*TPF*q: float4 shared and
         // global accesses with a 16-byte lane stride (conflict-free, fully coalesced).
         constexpr int n = N - 4;
         constexpr int CAP = TPF < 64 ? TPF : 64;
+        constexpr int BINS = N >= 1024 ? 1024 : 512;
         const int wf = t >> 5, lane = t & 31, nw = TPF / 32;
-        {   // bounds of the raw row (they bound every 5-bin mean), NaN flag; before the row barrier
-            const unsigned kmn = __reduce_min_sync(0xffffffffu, f2key(rmin));
-            const unsigned kmx = __reduce_max_sync(0xffffffffu, f2key(rmax));
+        {   // mean and spread of the raw row (warp partials; folded by every thread after the row barrier), NaN flag
+            float ws = rsum, wq = rsq;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                ws += __shfl_xor_sync(0xffffffffu, ws, o);
+                wq += __shfl_xor_sync(0xffffffffu, wq, o);
+            }
             if (lane == 0) {
-                atomicMin(&us[0], kmn);
-                atomicMax(&us[1], kmx);
+                fscr[wf] = ws;
+                fscr[16 + wf] = wq;
             }
             if (__any_sync(0xffffffffu, rnan) && lane == 0) atomicOr(&us[6], 1u);
         }
-        for (int b = t; b < 512; b += TPF) hist[b] = 0u;     // the exchange buffer is dead after the last pass
-        __syncthreads();                                     // B1: row complete, histograms clear, bounds known
+        for (int b = t; b < BINS / 4; b += TPF)                  // the exchange buffer is dead after the last pass
+            reinterpret_cast<uint4*>(hist)[b] = make_uint4(0u, 0u, 0u, 0u);
+        __syncthreads();                                     // B1: row complete, histogram clear, partials visible
         float s[16];
         unsigned b16[16];
         bool gvalid[4];
         {
-            const float lo = key2f(us[0]), hi = key2f(us[1]);
-            const float scale = hi > lo ? 65535.0f / (hi - lo) : 0.f;
+            // The median of any data lies within one standard deviation of its mean, and the 5-bin means have
+            // (up to edge terms) the raw row's mean and no more spread: BINS buckets over mean +- 1.25 sigma of
+            // the raw row put a handful of elements in the median's bucket.  The bucket function only has to
+            // be monotone -- whatever falls outside lands in the end buckets, and a crowded bucket takes the
+            // exact fallback below -- so the estimate affects speed, never the result.
+            float S = 0.f, Q = 0.f;
+            if constexpr (TPF >= 128) {
+#pragma unroll
+                for (int w = 0; w < TPF / 32; w += 4) {
+                    const float4 a = *reinterpret_cast<const float4*>(fscr + w);
+                    const float4 b = *reinterpret_cast<const float4*>(fscr + 16 + w);
+                    S += (a.x + a.y) + (a.z + a.w);
+                    Q += (b.x + b.y) + (b.z + b.w);
+                }
+            } else {
+#pragma unroll
+                for (int w = 0; w < TPF / 32; ++w) {
+                    S += fscr[w];
+                    Q += fscr[16 + w];
+                }
+            }
+            const float mean = S * (1.0f / N);
+            const float sd = sqrtf(fmaxf(Q * (1.0f / N) - mean * mean, 0.f));
+            const float lo = mean - 1.25f * sd;
+            const float scale = sd > 0.f ? (BINS / 2.5f) / sd : 0.f;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const int i0 = 4 * t + 4 * TPF * q;
@@ -127,57 +195,68 @@ __device__ __forceinline__ void smooth_epilogue(const float* __restrict__ row, f
                 for (int e = 0; e < 4; ++e) {
                     const float v = ((d[e] + d[e + 1]) + (d[e + 2] + d[e + 3]) + d[e + 4]) * 0.2f;
                     s[4 * q + e] = v;
-                    // monotone 16-bit bucket over the occupied dB range (NaN and negatives convert to 0)
-                    b16[4 * q + e] = min(65535u, __float2uint_rz((v - lo) * scale));
+                    // monotone bucket (NaN and values below the range convert to 0)
+                    b16[4 * q + e] = min((unsigned)(BINS - 1), __float2uint_rz((v - lo) * scale));
                 }
+                // unclamped smoothed row: the candidate ranking and the column resample read it (the clamp is
+                // applied on the fly there), this thread's own copy stays in registers
+                *reinterpret_cast<float4*>(srow + i0) = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
             }
         }
-        // exact lower/upper median: two 8-bit histogram levels over the linear buckets, then the few
-        // elements of the selected bucket are ranked directly (flat rows fall back to a key radix select)
-        unsigned rank = (unsigned)((n - 1) / 2), d0, d1, m;
+        // exact lower/upper median: one histogram over the buckets, then the few elements of the selected
+        // bucket are ranked directly (crowded buckets -- flat rows -- fall back to a key radix select)
+        unsigned rank = (unsigned)((n - 1) / 2), sel, m;
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             if (gvalid[q]) {
 #pragma unroll
-                for (int e = 0; e < 4; ++e) atomicAdd(&hist[b16[4 * q + e] >> 8], 1u);
+                for (int e = 0; e < 4; ++e) atomicAdd(&hist[b16[4 * q + e]], 1u);
             }
         __syncthreads();                                     // B2
-        hist_pick(hist, rank, d0, m, lane);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (gvalid[q]) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if ((b16[4 * q + e] >> 8) == d0) atomicAdd(&hist[256 + (b16[4 * q + e] & 255u)], 1u);
+#ifdef PSS_PICK_ALL_WARPS
+        hist_pick_wide<BINS>(hist, rank, sel, m, lane);      // measured variant: every warp scans, no barrier
+#else
+        if (wf == 0) {                                       // one warp scans the histogram for the frame
+            hist_pick_wide<BINS>(hist, rank, sel, m, lane);
+            if (lane == 0) {
+                us[8] = rank;
+                us[9] = sel;
+                us[10] = m;
             }
+        }
         __syncthreads();                                     // B3
-        hist_pick(hist + 256, rank, d1, m, lane);
-        const unsigned sel = (d0 << 8) | d1;
+        rank = us[8];
+        sel = us[9];
+        m = us[10];
+#endif
         const bool flat = m > (unsigned)CAP;
         {
-            const bool need_above = rank + 1u >= m;          // frame-uniform: upper median lies above the bucket
-            float fgt = INFINITY;
+            // the elements of the selected bucket: one bit per element, one slot claim per thread that has any
+            unsigned eqm = 0u;
 #pragma unroll
-            for (int q = 0; q < 4; ++q)
-                if (gvalid[q]) {
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const unsigned b = b16[4 * q + e];
-                        if (b == sel && !flat) {
-                            const unsigned slot = atomicAdd(&us[2], 1u);
-                            if (slot < (unsigned)CAP) cand[slot] = s[4 * q + e];
-                        }
-                        if (need_above && b > sel) fgt = fminf(fgt, s[4 * q + e]);
-                    }
+            for (int i = 0; i < 16; ++i) eqm |= (gvalid[i >> 2] && b16[i] == sel ? 1u : 0u) << i;
+            if (!flat && eqm) {
+                unsigned slot = atomicAdd(&us[2], (unsigned)__popc(eqm));
+                while (eqm) {
+                    const int i = __ffs(eqm) - 1;
+                    eqm &= eqm - 1u;
+                    if (slot < (unsigned)CAP) cand[slot] = srow[4 * t + 4 * TPF * (i >> 2) + (i & 3)];
+                    ++slot;
                 }
-            if (need_above) {
+            }
+            if (rank + 1u >= m) {                            // frame-uniform, rare: upper median lies above the bucket
+                float fgt = INFINITY;
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if (gvalid[i >> 2] && b16[i] > sel) fgt = fminf(fgt, s[i]);
                 const unsigned kgt = __reduce_min_sync(0xffffffffu, f2key(fgt));
                 if (lane == 0) atomicMin(&us[3], kgt);
             }
         }
         float v1, v2;
         if (!__syncthreads_or(flat)) {                       // B4
-            if ((unsigned)t < m) {
+#ifndef PSS_RANK_WARPS
+            if ((unsigned)t < m) {                           // thread t ranks candidate t against all (the other warps wait)
                 const float c = cand[t];
                 unsigned rk = 0;
                 for (unsigned j = 0; j < m; ++j) {
@@ -187,6 +266,23 @@ __device__ __forceinline__ void smooth_epilogue(const float* __restrict__ row, f
                 if (rk == rank) us[4] = __float_as_uint(c);
                 if (rk == rank + 1u) us[5] = __float_as_uint(c);
             }
+#else
+            {   // measured variant (slower: +2 % kernel time, the extra instructions of 7 more warps cost more than
+                // the one warp's serial chain): warp w ranks candidates w, w + nw, ... with ballots
+                const float o0 = (unsigned)lane < m ? cand[lane] : INFINITY;
+                const float o1 = (unsigned)lane + 32u < m ? cand[lane + 32] : INFINITY;
+                for (unsigned i = (unsigned)wf; i < m; i += (unsigned)nw) {
+                    const float c = cand[i];
+                    const bool p0 = (unsigned)lane < m && ((o0 < c) || (o0 == c && (unsigned)lane < i));
+                    const bool p1 = (unsigned)lane + 32u < m && ((o1 < c) || (o1 == c && (unsigned)lane + 32u < i));
+                    const unsigned rk = __popc(__ballot_sync(0xffffffffu, p0)) + (CAP > 32 ? __popc(__ballot_sync(0xffffffffu, p1)) : 0);
+                    if (lane == 0) {
+                        if (rk == rank) us[4] = __float_as_uint(c);
+                        if (rk == rank + 1u) us[5] = __float_as_uint(c);
+                    }
+                }
+            }
+#endif
             __syncthreads();                                 // B5
             v1 = __uint_as_float(us[4]);
             v2 = (n & 1) ? v1 : (rank + 1u < m ? __uint_as_float(us[5]) : key2f(us[3]));
@@ -253,7 +349,8 @@ __device__ __forceinline__ void smooth_epilogue(const float* __restrict__ row, f
         float thr = (float)(0.5 * ((double)v1 + (double)v2) - 10.0);
         const bool any_nan = us[6] != 0u;
         if (any_nan) thr = __int_as_float(0x7fc00000);       // np.median propagates NaN
-        // clamp, row statistics, store
+        // clamp, row statistics, store (measured: taking the statistics of the unclamped values early and
+        // redoing them only in threads that hold a value below the threshold is 0.5 % slower, not faster)
         float mx = -INFINITY, mn = INFINITY, fsum = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -268,35 +365,40 @@ __device__ __forceinline__ void smooth_epilogue(const float* __restrict__ row, f
                     fsum += v;
                 }
             }
-            const int i0 = 4 * t + 4 * TPF * q;
-            const float4 o = make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
-            *reinterpret_cast<float4*>(srow + i0) = o;
-            if (live && p.db && gvalid[q]) *reinterpret_cast<float4*>(p.db + frame * n + i0) = o;
+            if (live && p.db && gvalid[q])
+                *reinterpret_cast<float4*>(p.db + frame * n + 4 * t + 4 * TPF * q) =
+                    make_float4(s[4 * q], s[4 * q + 1], s[4 * q + 2], s[4 * q + 3]);
         }
-        mx = warp_max(mx);
-        mn = warp_min(mn);
-        const double dsum = warp_sum((double)fsum);
-        if (lane == 0) {
-            fscr[wf] = mx;
-            fscr[16 + wf] = mn;
-            dscr[wf] = dsum;
-        }
-        __syncthreads();                                     // B6: clamped row + warp partials visible
-        if (live && p.stats && t == 0) {
-            float a = fscr[0], b = fscr[16];
-            double sm = dscr[0];
-            for (int w = 1; w < nw; ++w) {
-                a = fmaxf(a, fscr[w]);
-                b = fminf(b, fscr[16 + w]);
-                sm += dscr[w];
+        if (live && p.stats) {
+            // warp partials, then the last warp to arrive (a shared counter, no CTA barrier) folds them
+            const unsigned kx = __reduce_max_sync(0xffffffffu, f2key(mx));
+            const unsigned kn = __reduce_min_sync(0xffffffffu, f2key(mn));
+            const double dsum = warp_sum((double)fsum);
+            if (lane == 0) {
+                fscr[wf] = key2f(kx);
+                fscr[16 + wf] = key2f(kn);
+                dscr[wf] = dsum;
+                __threadfence_block();
+                if (atomicAdd(&us[7], 1u) == (unsigned)(nw - 1)) {
+                    __threadfence_block();
+                    const volatile float* vf = fscr;
+                    const volatile double* vd = dscr;
+                    float a = vf[0], b = vf[16];
+                    double sm = vd[0];
+                    for (int w = 1; w < nw; ++w) {
+                        a = fmaxf(a, vf[w]);
+                        b = fminf(b, vf[16 + w]);
+                        sm += vd[w];
+                    }
+                    const float nanv = __int_as_float(0x7fc00000);
+                    float4 st;
+                    st.x = any_nan ? nanv : a;                    // np.max
+                    st.y = any_nan ? nanv : (float)(sm / n);      // np.mean
+                    st.z = b;                                     // finite min
+                    st.w = a;                                     // finite max
+                    reinterpret_cast<float4*>(p.stats)[frame] = st;
+                }
             }
-            const float nanv = __int_as_float(0x7fc00000);
-            float4 st;
-            st.x = any_nan ? nanv : a;                    // np.max
-            st.y = any_nan ? nanv : (float)(sm / n);      // np.mean
-            st.z = b;                                     // finite min
-            st.w = a;                                     // finite max
-            reinterpret_cast<float4*>(p.stats)[frame] = st;
         }
         if (live && p.cols) {
             const int W = p.W;
@@ -307,8 +409,12 @@ __device__ __forceinline__ void smooth_epilogue(const float* __restrict__ row, f
                 float o;
                 if (j >= n - 1) {
                     o = srow[n - 1];
+                    if (o < thr) o = thr;
                 } else {
-                    const double y0 = srow[j], y1 = srow[j + 1];
+                    float f0 = srow[j], f1 = srow[j + 1];
+                    if (f0 < thr) f0 = thr;
+                    if (f1 < thr) f1 = thr;
+                    const double y0 = f0, y1 = f1;
                     o = (float)((y1 - y0) * (x - (double)j) + y0);
                 }
                 p.cols[frame * W + c] = o;
@@ -369,11 +475,13 @@ __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<
 // LOG2N1 > 0: this launch is the second stage of a length N*2^LOG2N1 transform (four-step FFT): frame
 // index = big_frame * N1 + k1, input = column-transformed, twiddled fp64 rows, output bin = k1 + N1*k2.
 template <int LOG2N, typename T, int EPI, int LOG2N1 = 0>
-// Occupancy of the 64 KB-per-CTA configurations: 2 CTAs/SM at ~110-120 registers for every variant
-// (PSS_SMOOTH_MINB).  With the 13-barrier key radix select the smoothing variant was faster at 3 CTAs/SM
-// held to 80 registers; with the 6-barrier two-level median 2 CTAs/SM wins by 6 %.
+// Occupancy of the 64 KB-per-CTA configurations: 2 CTAs/SM at ~110-120 registers for the raw / scanner
+// variants.  The smoothing variant went back and forth with its median: 3 CTAs/SM at 80 registers with the
+// 13-barrier key radix select, 2 CTAs/SM (+6 %) with the 6-barrier two-level histogram, and 3 CTAs/SM again
+// (+2.5 % at 4096 points, +3 % at 1024, -2 % at 2048: pss_smooth_minb) with the 5-barrier single-histogram
+// median below; `tools/build_variant.sh minb2 -DPSS_SMOOTH_MINB=2` rebuilds the other side of the comparison.
 __global__ void __launch_bounds__(PsdCfg<LOG2N, T>::THREADS,
-                                  (EPI == EPI_SMOOTH && PsdCfg<LOG2N, T>::MINB == 2) ? PSS_SMOOTH_MINB : PsdCfg<LOG2N, T>::MINB)
+                                  (EPI == EPI_SMOOTH && PsdCfg<LOG2N, T>::MINB == 2) ? pss_smooth_minb(LOG2N) : PsdCfg<LOG2N, T>::MINB)
 psd_kernel(const PsdParams p) {
     using C = PsdCfg<LOG2N, T>;
     constexpr int N = C::N, TPF = C::TPF, NP = C::NP;
@@ -398,7 +506,7 @@ psd_kernel(const PsdParams p) {
     // frame-local scratch that aliases the exchange buffer once the last pass has read it
     float* row = reinterpret_cast<float*>(buf);           // [N] dB, fft-shifted
     float* srow = row + N;                                // [N] smoothed / clamped
-    unsigned* hist = reinterpret_cast<unsigned*>(srow + N);   // [2][256] (rare path: [4][256])
+    unsigned* hist = reinterpret_cast<unsigned*>(srow + N);   // [1024] bins (rare path: [4][256])
     static_assert(EPI == EPI_RAW || N >= 512, "epilogues need N >= 512");
     constexpr bool SM = EPI == EPI_SMOOTH;
     __shared__ unsigned us_s[SM ? C::FPC : 1][16];        // [0]=raw kmin [1]=raw kmax [2]=#cand [3]=min key above [4]=v1 [5]=v2 [6]=nan
@@ -406,7 +514,7 @@ psd_kernel(const PsdParams p) {
     __shared__ float cand_s[SM ? C::FPC : 1][SM ? C::CAP : 1];
     constexpr int FS = EPI == EPI_RAW ? 1 : C::FPC;
     __shared__ double dscr_s[FS][16];                     // per-warp sums
-    __shared__ float fscr_s[FS][32];                      // per-warp max / min
+    __shared__ __align__(16) float fscr_s[FS][32];        // per-warp max / min (and the raw row's sum / sum of squares)
     __shared__ unsigned uscr_s[FS][16];                   // scanner partial counts
     double* dscr = dscr_s[EPI == EPI_RAW ? 0 : f];
     float* fscr = fscr_s[EPI == EPI_RAW ? 0 : f];
@@ -415,7 +523,7 @@ psd_kernel(const PsdParams p) {
         if (t < 16) us_s[f][t] = (t == 0 || t == 3) ? 0xffffffffu : 0u;
         if (t < 8) uf_s[f][t] = (t == 0 || t == 3) ? 0xffffffffu : 0u;
     }
-    float rmin = INFINITY, rmax = -INFINITY;              // EPI_SMOOTH: bounds / NaN flag of this thread's raw dB values
+    float rsum = 0.f, rsq = 0.f;                          // EPI_SMOOTH: sum, sum of squares, NaN flag of this thread's raw dB values
     bool rnan = false;
     __shared__ double mom_s[C::THREADS / 32][3];
 
@@ -516,8 +624,8 @@ psd_kernel(const PsdParams p) {
             reinterpret_cast<double*>(buf)[pos] = pw;        // fp64 power row (the exchange buffer is dead)
         } else {
             row[pos] = d;
-            rmin = fminf(rmin, d);
-            rmax = fmaxf(rmax, d);
+            rsum += d;
+            rsq = fmaf(d, d, rsq);
             rnan |= d != d;
         }
     };
@@ -569,8 +677,9 @@ psd_kernel(const PsdParams p) {
         }
     }
 
-    if constexpr (EPI == EPI_SMOOTH)
-        smooth_epilogue<N, TPF>(row, srow, hist, us_s[f], uf_s[f], cand_s[f], dscr, fscr, rmin, rmax, rnan, t, live, frame, p);
+    if constexpr (EPI == EPI_SMOOTH) {
+        smooth_epilogue<N, TPF>(row, srow, hist, us_s[f], uf_s[f], cand_s[f], dscr, fscr, rsum, rsq, rnan, t, live, frame, p);
+    }
 }
 
 
@@ -596,23 +705,23 @@ psd_epilogue_kernel(const PsdEpiParams q) {
     __shared__ unsigned us[16], uf[8];
     __shared__ float cand[64];
     __shared__ double dscr[16];
-    __shared__ float fscr[32];
+    __shared__ __align__(16) float fscr[32];
     const int t = threadIdx.x;
     const long long frame = blockIdx.x;
     if (t < 16) us[t] = (t == 0 || t == 3) ? 0xffffffffu : 0u;
     if (t < 8) uf[t] = (t == 0 || t == 3) ? 0xffffffffu : 0u;
     const float4* src = reinterpret_cast<const float4*>(q.raw + frame * N);
-    float rmin = INFINITY, rmax = -INFINITY;
+    float rsum = 0.f, rsq = 0.f;
     bool rnan = false;
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const float4 v = __ldcs(src + t + g * TPF);
         reinterpret_cast<float4*>(row)[t + g * TPF] = v;
-        rmin = fminf(fminf(rmin, v.x), fminf(fminf(v.y, v.z), v.w));
-        rmax = fmaxf(fmaxf(rmax, v.x), fmaxf(fmaxf(v.y, v.z), v.w));
+        rsum += (v.x + v.y) + (v.z + v.w);
+        rsq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, rsq))));
         rnan |= (v.x != v.x) | (v.y != v.y) | (v.z != v.z) | (v.w != v.w);
     }
-    smooth_epilogue<N, TPF>(row, srow, hist, us, uf, cand, dscr, fscr, rmin, rmax, rnan, t, true, frame, q.out);
+    smooth_epilogue<N, TPF>(row, srow, hist, us, uf, cand, dscr, fscr, rsum, rsq, rnan, t, true, frame, q.out);
 }
 
 // ---------------------------------------------------------------------------------- large transforms
@@ -1244,7 +1353,7 @@ static int launch_one(pss_ctx* ctx, const PsdParams& p) {
         PSS_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
     const long long grid = (p.n_frames + C::FPC - 1) / C::FPC;
     PsdParams q = p;
-    q.ahead = ctx->sm_count * ((EPI == EPI_SMOOTH && C::MINB == 2) ? PSS_SMOOTH_MINB : C::MINB);
+    q.ahead = ctx->sm_count * ((EPI == EPI_SMOOTH && C::MINB == 2) ? pss_smooth_minb(LOG2N) : C::MINB);
     if (q.W > 1) q.col_step = (double)(C::N - 4 - 1) / (double)(q.W - 1);
     kern<<<(unsigned)grid, C::THREADS, C::SMEM, ctx->stream>>>(q);
     PSS_LAUNCH_CHECK(ctx);
