@@ -94,6 +94,45 @@ def test_psd_epilogue_clamp_fires_and_mixed_batch(ctx):
         assert fired >= 4
 
 
+def _shaped(n, shape, seed):
+    """IQ whose un-windowed spectrum has a designed dB profile (random phases), so the median select sees
+    distributions the signal generators do not produce."""
+    rng = np.random.default_rng(seed)
+    k = np.arange(n)
+    if shape == "bimodal":                       # half the bins 60 dB above the rest, a notch far below: clamp fires
+        db = np.where(k < n // 2, 0.0, -60.0) + rng.normal(0, 1.0, n)
+        db[n // 8:n // 8 + n // 16] = -110.0
+    elif shape == "heavy_tail":                  # a few enormous outliers blow the row's sigma up: crowded buckets
+        db = rng.normal(-40.0, 0.05, n)
+        db[rng.choice(n, 6, replace=False)] = 40.0
+        db[rng.choice(n, 6, replace=False)] = -95.0
+    elif shape == "staircase":                   # plateaus of nearly equal values around the median
+        db = -30.0 - 5.0 * np.floor(8.0 * k / n) + rng.normal(0, 1e-4, n)
+    elif shape == "skewed":                      # exponential tail: median well below the mean
+        db = -80.0 + rng.exponential(12.0, n)
+    else:
+        raise ValueError(shape)
+    spec = 10.0 ** (db / 20.0) * np.exp(2j * np.pi * rng.random(n))
+    return np.fft.ifft(np.fft.ifftshift(spec)).astype(np.complex64)
+
+
+@pytest.mark.parametrize("n", [512, 4096, 8192])
+def test_psd_epilogue_designed_distributions(ctx, n):
+    """The single-histogram median places its buckets from the raw row's mean and spread; rows whose median
+    sits far from the mean, whose spread is dominated by outliers, or whose values pile up in a few buckets
+    must come out the same (the estimate may only cost time)."""
+    shapes = ["bimodal", "heavy_tail", "staircase", "skewed", "bimodal", "staircase"]
+    for window in ("none", "hamming"):
+        x = np.stack([_shaped(n, sh, 70 + i) for i, sh in enumerate(shapes)])
+        res = ctx.psd(x, window=window, epilogue=True, W=101, want_stats=True)
+        for f in range(len(x)):
+            want = O.psd_epilogue(O.psd_db(x[f], window=window))
+            assert np.max(np.abs(res["db"][f] - want)) <= TOL_DB, (n, window, shapes[f])
+            assert np.max(np.abs(res["cols"][f] - O.resample_cols(want, 101))) <= TOL_DB
+            pk, av = O.peak_avg(want)
+            assert abs(res["stats"][f][0] - pk) <= TOL_DB and abs(res["stats"][f][1] - av) <= TOL_DB
+
+
 def test_psd_epilogue_constant_row(ctx):
     # all-zero input: every bin is exactly -100 dB, the median select sees all-equal keys
     res = ctx.psd(np.zeros((2, 1024), np.complex64), epilogue=True, want_stats=True)
