@@ -837,16 +837,17 @@ psd_colfft_big_kernel(const float2* __restrict__ iq, const double* __restrict__ 
 
 // Row epilogue for rows that do not fit one CTA's shared memory: the same 5-bin smoothing, exact
 // median clamp, statistics and W-column resample as EPI_SMOOTH, streaming the row from L2.
-__device__ __forceinline__ bool row_median2_512(const float* __restrict__ srow, const int n, const float lo,
-                                                const float hi, unsigned* hist, unsigned* us, float* cand,
-                                                float& v1, float& v2);
+__device__ __forceinline__ bool row_median1_512(const float* __restrict__ srow, const int n, const float* pst,
+                                                unsigned* hist, unsigned* us, float* cand, float& v1, float& v2);
+__device__ __forceinline__ void row_stats_512(float rsum, float rsq, float* pst);
 
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(512, 2)
 row_epilogue_kernel(const float* __restrict__ raw, const int N, const long long n_frames, float* __restrict__ db,
                     float* __restrict__ cols, const int W, float* __restrict__ stats) {
-    __shared__ unsigned hist[512];
-    __shared__ unsigned us[8], ub[2];
-    __shared__ float cand[64];
+    __shared__ unsigned hist[1024];
+    __shared__ unsigned us[16];
+    __shared__ __align__(16) float cand[64];
+    __shared__ __align__(16) float pst[32];
     __shared__ double dsum[16];
     __shared__ float fmx[16], fmn[16];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -854,30 +855,22 @@ row_epilogue_kernel(const float* __restrict__ raw, const int N, const long long 
     for (long long f = blockIdx.x; f < n_frames; f += gridDim.x) {
         const float* d = raw + f * N;
         float* s = db + f * n;
-        if (tid < 8) us[tid] = tid == 3 ? 0xffffffffu : 0u;
-        if (tid < 2) ub[tid] = tid == 0 ? 0xffffffffu : 0u;
+        if (tid < 16) us[tid] = tid == 3 ? 0xffffffffu : 0u;
         __syncthreads();
-        // 5-bin means; the raw row's min / max bound them (linear buckets of the 2-level median)
-        float rlo = INFINITY, rhi = -INFINITY;
+        // 5-bin means; their mean and spread place the buckets of the median's histogram
+        float rsum = 0.f, rsq = 0.f;
         bool has_nan = false;
         for (int i = tid; i < n; i += 512) {
             const float v = ((d[i] + d[i + 1]) + (d[i + 2] + d[i + 3]) + d[i + 4]) * 0.2f;
             s[i] = v;
-            rlo = fminf(rlo, fminf(d[i], d[i + 4]));
-            rhi = fmaxf(rhi, fmaxf(d[i], d[i + 4]));
+            rsum += v;
+            rsq = fmaf(v, v, rsq);
             has_nan |= (v != v);
         }
-        {
-            const unsigned klo = __reduce_min_sync(0xffffffffu, f2key(rlo));
-            const unsigned khi = __reduce_max_sync(0xffffffffu, f2key(rhi));
-            if (lane == 0) {
-                atomicMin(&ub[0], klo);
-                atomicMax(&ub[1], khi);
-            }
-        }
+        row_stats_512(rsum, rsq, pst);
         const bool any_nan = __syncthreads_or(has_nan);
         float v1, v2;
-        if (!row_median2_512(s, n, key2f(ub[0]), key2f(ub[1]), hist, us, cand, v1, v2)) {
+        if (!row_median1_512(s, n, pst, hist, us, cand, v1, v2)) {
             unsigned ka, kb;
             row_select2_512(s, n, (unsigned)((n - 1) / 2), hist, us, ka, kb);
             v1 = key2f(ka);
@@ -950,48 +943,102 @@ row_epilogue_kernel(const float* __restrict__ raw, const int N, const long long 
 //   epilogue (EPI_SMOOTH): the raw dB row comes back from L2, the smoothed row is kept in the
 //            128 KB of shared memory the transforms no longer need (N <= 32768) and the exact
 //            median / clamp / statistics / resample run on it.
-// Exact lower/upper median of a row of n floats (shared or L2-resident), all 512 threads of the CTA:
-// two 8-bit histogram levels over 65536 linear buckets of [lo, hi] (any bounds of the row), then the
-// few elements of the selected bucket are ranked directly.  Returns false (CTA-uniform) when the bucket
-// holds more than 64 elements (flat rows); the caller then runs the key radix select.
-// hist [512], us [8] ([2] = 0, [3] = 0xffffffff on entry), cand [64] are shared scratch.
-__device__ __forceinline__ bool row_median2_512(const float* __restrict__ srow, const int n, const float lo,
-                                                const float hi, unsigned* hist, unsigned* us, float* cand,
-                                                float& v1, float& v2) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    const float scale = hi > lo ? 65535.0f / (hi - lo) : 0.f;
-    hist[tid] = 0u;
-    __syncthreads();
-    for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
-        const float4 v = *reinterpret_cast<const float4*>(srow + i0);
-        atomicAdd(&hist[min(65535u, __float2uint_rz((v.x - lo) * scale)) >> 8], 1u);
-        atomicAdd(&hist[min(65535u, __float2uint_rz((v.y - lo) * scale)) >> 8], 1u);
-        atomicAdd(&hist[min(65535u, __float2uint_rz((v.z - lo) * scale)) >> 8], 1u);
-        atomicAdd(&hist[min(65535u, __float2uint_rz((v.w - lo) * scale)) >> 8], 1u);
-    }
-    __syncthreads();
-    unsigned rank = (unsigned)((n - 1) / 2), d0, d1, m;
-    hist_pick(hist, rank, d0, m, lane);
-    for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
-        const float4 v = *reinterpret_cast<const float4*>(srow + i0);
-        const float e[4] = {v.x, v.y, v.z, v.w};
+// Per-warp partials of a row's sum and sum of squares (pst[0..15], pst[16..31]); the caller's next CTA
+// barrier publishes them.
+__device__ __forceinline__ void row_stats_512(float rsum, float rsq, float* pst) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const unsigned b = min(65535u, __float2uint_rz((e[q] - lo) * scale));
-            if ((b >> 8) == d0) atomicAdd(&hist[256 + (b & 255u)], 1u);
-        }
+    for (int o = 16; o > 0; o >>= 1) {
+        rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+        rsq += __shfl_xor_sync(0xffffffffu, rsq, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        pst[threadIdx.x >> 5] = rsum;
+        pst[16 + (threadIdx.x >> 5)] = rsq;
+    }
+}
+
+// Exact lower/upper median of a row of n floats (shared or L2-resident), all 512 threads of the CTA.  Every
+// value maps monotonically to a 20-bit key over mean +- 1.1 sigma of the row (pst: the per-warp partials
+// above, taken over the smoothed values themselves, so the median is inside; values outside land in the end
+// keys).  One 1024-bin histogram of the upper 10 bits, scanned by one warp; if the selected bucket holds more
+// than 64 elements (rows beyond ~64 k bins) a second histogram of the lower 10 bits inside it; then the few
+// elements left are ranked directly.  Returns false (CTA-uniform) when even that bucket holds more than 64
+// elements (flat rows); the caller then runs the key radix select.
+// hist [1024], us [16] ([2] = 0, [3] = 0xffffffff on entry), cand [64] are shared scratch.
+__device__ __forceinline__ bool row_median1_512(const float* __restrict__ srow, const int n, const float* pst,
+                                                unsigned* hist, unsigned* us, float* cand, float& v1, float& v2) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    float S = 0.f, Q = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; w += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(pst + w);
+        const float4 b = *reinterpret_cast<const float4*>(pst + 16 + w);
+        S += (a.x + a.y) + (a.z + a.w);
+        Q += (b.x + b.y) + (b.z + b.w);
+    }
+    const float inv = 1.0f / (float)n;
+    const float mean = S * inv, var = Q * inv - mean * mean;
+    const float scale = var > 0.f ? (1048576 / 2.2f) * rsqrtf(var) : 0.f;
+    const float off = var > 0.f ? fmaf(-mean, scale, 524288.0f) : 0.f;
+    auto key = [&](const float v) { return min(1048575u, __float2uint_rz(fmaf(v, scale, off))); };
+    hist[tid] = 0u;
+    hist[tid + 512] = 0u;
+    if (tid < 64) cand[tid] = INFINITY;
+    __syncthreads();
+    // (measured: counting the out-of-range quarter of a Gaussian row in registers instead of in the two end
+    // buckets is slower -- the branches cost more than the contended atomics)
+    for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
+        const float4 v = *reinterpret_cast<const float4*>(srow + i0);
+        atomicAdd(&hist[key(v.x) >> 10], 1u);
+        atomicAdd(&hist[key(v.y) >> 10], 1u);
+        atomicAdd(&hist[key(v.z) >> 10], 1u);
+        atomicAdd(&hist[key(v.w) >> 10], 1u);
     }
     __syncthreads();
-    hist_pick(hist + 256, rank, d1, m, lane);
-    if (m > 64u) return false;
-    const unsigned sel = (d0 << 8) | d1;
+    auto pick = [&](unsigned r_in) {                         // one warp scans, everyone reads (rank, bin, count)
+        if (tid < 32) {
+            unsigned r = r_in, d, c;
+            hist_pick_wide<1024>(hist, r, d, c, lane);
+            if (lane == 0) {
+                us[8] = r;
+                us[9] = d;
+                us[10] = c;
+            }
+        }
+        __syncthreads();
+    };
+    pick((unsigned)((n - 1) / 2));
+    unsigned rank = us[8], sel = us[9], m = us[10];
+    int shift = 10;
+    if (m > 64u) {                                           // CTA-uniform
+        __syncthreads();                                     // everyone has read us[8..10]
+        hist[tid] = 0u;
+        hist[tid + 512] = 0u;
+        __syncthreads();
+        for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
+            const float4 v = *reinterpret_cast<const float4*>(srow + i0);
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned k = key(e[q]);
+                if ((k >> 10) == sel) atomicAdd(&hist[k & 1023u], 1u);
+            }
+        }
+        __syncthreads();
+        pick(rank);
+        rank = us[8];
+        sel = (sel << 10) | us[9];
+        m = us[10];
+        shift = 0;
+        if (m > 64u) return false;
+    }
     unsigned kgt = 0xffffffffu;
     for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
         const float4 v = *reinterpret_cast<const float4*>(srow + i0);
         const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const unsigned b = min(65535u, __float2uint_rz((e[q] - lo) * scale));
+            const unsigned b = key(e[q]) >> shift;
             if (b == sel) {
                 const unsigned slot = atomicAdd(&us[2], 1u);
                 if (slot < 64u) cand[slot] = e[q];
@@ -1005,9 +1052,12 @@ __device__ __forceinline__ bool row_median2_512(const float* __restrict__ srow, 
     if ((unsigned)tid < m) {
         const float c = cand[tid];
         unsigned rk = 0;
-        for (unsigned j = 0; j < m; ++j) {
-            const float o = cand[j];
-            rk += (o < c) || (o == c && j < (unsigned)tid);
+        for (unsigned j = 0; j < m; j += 4) {                // slots >= m hold +inf: they never count
+            const float4 o = *reinterpret_cast<const float4*>(cand + j);
+            rk += (o.x < c) || (o.x == c && j < (unsigned)tid);
+            rk += (o.y < c) || (o.y == c && j + 1 < (unsigned)tid);
+            rk += (o.z < c) || (o.z == c && j + 2 < (unsigned)tid);
+            rk += (o.w < c) || (o.w == c && j + 3 < (unsigned)tid);
         }
         if (rk == rank) us[4] = __float_as_uint(c);
         if (rk == rank + 1u) us[5] = __float_as_uint(c);
@@ -1016,6 +1066,14 @@ __device__ __forceinline__ bool row_median2_512(const float* __restrict__ srow, 
     v1 = __uint_as_float(us[4]);
     v2 = (n & 1) ? v1 : (rank + 1u < m ? __uint_as_float(us[5]) : key2f(us[3]));
     return true;
+}
+
+// The same as a real call: the 32768-point fused kernel sits at its 128-register limit and spills in the
+// transform loops when the median is inlined into it (measured 1.98 inlined vs 1.80 ms per GiB called; the
+// other sizes are faster inlined).
+__device__ __noinline__ bool row_median1_512_call(const float* __restrict__ srow, const int n, const float* pst,
+                                                  unsigned* hist, unsigned* us, float* cand, float& v1, float& v2) {
+    return row_median1_512(srow, n, pst, hist, us, cand, v1, v2);
 }
 
 // L2 residency control for the fused large transforms: the per-CTA scratch (fp64 rows, raw dB row) is
@@ -1084,9 +1142,10 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
     constexpr bool SROW_SMEM = (size_t)N * 4 <= 2 * fft_padded(N2) * sizeof(cx<double>);
     static_assert((N2 / 512) % CL == 0 && (N1 / 2) % CL == 0, "columns and row pairs must split evenly over the cluster");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ unsigned hist[512];
-    __shared__ unsigned us[8], ub[2];
-    __shared__ float cand[64];
+    __shared__ unsigned hist[1024];
+    __shared__ unsigned us[16];
+    __shared__ __align__(16) float cand[64];
+    __shared__ __align__(16) float pst[32];
     __shared__ double dsum_s[16];
     __shared__ float fmx_s[16], fmn_s[16];
     __shared__ double mom_s[16][3];
@@ -1115,8 +1174,7 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
         }
         float* raw = EPI == EPI_SMOOTH ? (FPG == 1 ? rawbase : rawbase + (size_t)j * N) : nullptr;
         if constexpr (EPI == EPI_SMOOTH && CL == 1) {    // one CTA per frame: reset the median scratch ahead of the barriers below
-            if (tid < 8) us[tid] = tid == 3 ? 0xffffffffu : 0u;
-            if (tid < 2) ub[tid] = tid == 0 ? 0xffffffffu : 0u;      // raw-row bounds (keys)
+            if (tid < 16) us[tid] = tid == 3 ? 0xffffffffu : 0u;
         }
         // ---- stage A: column DFTs of this CTA's share of the columns
         const float2* src = p.iq + frame * N;
@@ -1229,42 +1287,32 @@ __global__ void __launch_bounds__(512, 1) psd_large_kernel(const PsdLargeParams 
         if (CL == 1 || frame < p.n_frames) {
             float* raw = CL == 1 ? rawbase : rawbase + (size_t)rank * N;
             if (CL > 1) {
-                if (tid < 8) us[tid] = tid == 3 ? 0xffffffffu : 0u;
-                if (tid < 2) ub[tid] = tid == 0 ? 0xffffffffu : 0u;  // raw-row bounds (keys)
+                if (tid < 16) us[tid] = tid == 3 ? 0xffffffffu : 0u;
                 __syncthreads();
             }
         {
             float* srow = SROW_SMEM ? reinterpret_cast<float*>(smem_raw) : p.srow2 + (size_t)blockIdx.x * N;
             bool has_nan = false;
-            float rlo = INFINITY, rhi = -INFINITY;
+            float rsum = 0.f, rsq = 0.f;
             for (int i0 = 4 * tid; i0 < n; i0 += 2048) {
                 const float4 a = ld_keep(reinterpret_cast<const float4*>(raw + i0), keep);
                 const float4 c = ld_keep(reinterpret_cast<const float4*>(raw + i0 + 4), keep);     // i0 + 4 <= N - 4
                 const float d[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
                 float sv[4];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    rlo = fminf(rlo, d[e]);
-                    rhi = fmaxf(rhi, d[e]);
-                }
-#pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     sv[e] = ((d[e] + d[e + 1]) + (d[e + 2] + d[e + 3]) + d[e + 4]) * 0.2f;
                     has_nan |= sv[e] != sv[e];
+                    rsum += sv[e];
+                    rsq = fmaf(sv[e], sv[e], rsq);
                 }
                 *reinterpret_cast<float4*>(srow + i0) = make_float4(sv[0], sv[1], sv[2], sv[3]);
             }
-            {
-                const unsigned klo = __reduce_min_sync(0xffffffffu, f2key(rlo));
-                const unsigned khi = __reduce_max_sync(0xffffffffu, f2key(rhi));
-                if (lane == 0) {
-                    atomicMin(&ub[0], klo);
-                    atomicMax(&ub[1], khi);
-                }
-            }
+            row_stats_512(rsum, rsq, pst);
             const bool any_nan = __syncthreads_or(has_nan);
             float v1, v2;
-            if (!row_median2_512(srow, n, key2f(ub[0]), key2f(ub[1]), hist, us, cand, v1, v2)) {
+            if (!(LOG2N == 15 ? row_median1_512_call(srow, n, pst, hist, us, cand, v1, v2)
+                              : row_median1_512(srow, n, pst, hist, us, cand, v1, v2))) {
                 unsigned ka, kb;
                 row_select2_512(srow, n, (unsigned)((n - 1) / 2), hist, us, ka, kb);
                 v1 = key2f(ka);
