@@ -28,6 +28,11 @@ int pss_reserve(pss_ctx* ctx, void** p, size_t* have, size_t need) {
     return PSS_OK;
 }
 
+bool pss_use_pdl() {
+    static const bool on = getenv("PSS_PDL") && atoi(getenv("PSS_PDL")) != 0;
+    return on;
+}
+
 void pss_demod_release(pss_ctx* ctx);     // pss_demod.cu
 void pss_display_release(pss_ctx* ctx);   // pss_display.cu
 

@@ -83,6 +83,33 @@ int pss_fail_cuda(pss_ctx* ctx, cudaError_t e, const char* what, const char* fil
         (ctx)->launches++;                                                           \
     } while (0)
 
+// Programmatic dependent launch (PSS_PDL=1): the kernels of the bench step's chain -- PSD, display render, iq-correction
+// coefficients, forcing, scan -- are launched with the programmatic-stream-serialisation attribute.  Each of them runs
+// its prologue (tables into shared memory, barrier set-up), then `griddepcontrol.wait` (the previous kernel of the
+// stream has completed and its writes are visible), then `griddepcontrol.launch_dependents`, so that the next
+// kernel's CTAs are scheduled while this one drains and meet their own wait with the prologue already done.  Without
+// the attribute both instructions do nothing.
+bool pss_use_pdl();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t pss_launch(void (*kern)(KArgs...), const unsigned grid, const unsigned block, const size_t smem,
+                                     cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pss_use_pdl() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+__device__ __forceinline__ void pss_grid_dependency_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // geometry of an open display stream (pss_display.cu); PSS_ERR_ARG if it does not exist
 int pss_display_geom(const pss_ctx* ctx, int stream, int* W, int* rows_max);
 

@@ -27,6 +27,7 @@
 // iq_correction's estimates (signal_processing.py:52-64) from the block's second moments.
 __global__ void demod_corr_kernel(const double* __restrict__ moments, const int mom_fpb, const int N,
                                   const long long n_frames, float4* __restrict__ corr) {
+    pss_grid_dependency_sync();       // PSS_PDL: the moments come from the previous kernel of the stream
     const long long f = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= n_frames) return;
     double a = 0, b = 0, c = 0;
@@ -356,6 +357,7 @@ demod_force_fused_kernel(const DecimDev D, const float2* __restrict__ iq, const 
         tab = ts;
         __syncthreads();
     }
+    pss_grid_dependency_sync();       // PSS_PDL: the table is in shared memory; corr / the scratch belong to earlier kernels
     const double* trow = tab + (size_t)D.KS * NTD * 32;               // [KS][4]: r-row taps
     const int q = D.q, CS = D.CS;
     const int sgroups = (D.groups + U - 1) / U;                       // super-groups of U * 8 chunks per block
@@ -502,6 +504,7 @@ demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __rest
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pss_grid_dependency_sync();       // PSS_PDL: tables copied, barrier initialised; the forcing rows belong to the previous kernel
     unsigned phase = 0;
     const double *Gm = tabs + T.G(), *CR = tabs + T.CR(), *CB = tabs + T.CB();
     const double *BF = tabs + T.BF(), *PWF = tabs + T.PWF(), *BBk = tabs + T.BB(), *PWB = tabs + T.PWB();
@@ -828,7 +831,7 @@ static int launch_force(pss_ctx* ctx, pss_demod_plan* pl, const float2* iq, long
     } else if (tb) {
         auto k = demod_force_fused_kernel<SF, true>;
         PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
-        k<<<(unsigned)g1, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, F, corr);
+        PSS_CUDA(ctx, pss_launch(k, (unsigned)g1, (unsigned)FORCE_THREADS, (size_t)tb, ctx->stream, D, iq, (int)nf, F, corr));
     } else {
         demod_force_fused_kernel<SF, false><<<(unsigned)g1, FORCE_THREADS, 0, ctx->stream>>>(D, iq, (int)nf, F, corr);
     }
@@ -843,7 +846,7 @@ static int launch_scan(pss_ctx* ctx, pss_demod_plan* pl, const float2* iq, long 
     auto ks = D.scan_slot_smem ? demod_scan_kernel<SF, true> : demod_scan_kernel<SF, false>;
     PSS_CUDA(ctx, cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, D.scan_smem));
     long long g2 = nf < 16LL * ctx->sm_count ? nf : 16LL * ctx->sm_count;
-    ks<<<(unsigned)g2, SCAN_THREADS, D.scan_smem, st>>>(D, iq, audio, (int)nf, F, corr);
+    PSS_CUDA(ctx, pss_launch(ks, (unsigned)g2, (unsigned)SCAN_THREADS, (size_t)D.scan_smem, st, D, iq, audio, (int)nf, F, corr));
     PSS_LAUNCH_CHECK(ctx);
     return PSS_OK;
 }
@@ -887,8 +890,8 @@ int pss_decim_launch(pss_ctx* ctx, pss_demod_plan* pl, const float* iq, int64_t 
             moments = (const double*)pl->mom_scratch;
             mom_fpb = 1;
         }
-        demod_corr_kernel<<<(unsigned)((n_frames + 127) / 128), 128, 0, ctx->stream>>>(moments, mom_fpb, D.N, n_frames,
-                                                                                       (float4*)pl->corr);
+        PSS_CUDA(ctx, pss_launch(demod_corr_kernel, (unsigned)((n_frames + 127) / 128), 128u, 0, ctx->stream, moments, mom_fpb, D.N,
+                                 (long long)n_frames, (float4*)pl->corr));
         PSS_LAUNCH_CHECK(ctx);
         corr = (const float4*)pl->corr;
     }

@@ -87,6 +87,7 @@ struct RenderArgs {
 // PLANES = false: the lean instantiation for callers that only want the normalised values (the bench step).
 template <typename T, bool PLANES>
 __global__ void __launch_bounds__(256) display_render_kernel(const RenderArgs<T> A) {
+    pss_grid_dependency_sync();                        // PSS_PDL: the rows come from the previous kernel of the stream
     const long long r = blockIdx.x;
     const long long t = A.first + r * A.step;          // newest frame of this render
     if (t < 0 || t >= A.n_frames) return;
@@ -529,8 +530,8 @@ static void persistence_colours(int rows_max, int* out) {
 template <typename T>
 static int run_render(pss_ctx* ctx, DisplayRing* ring, RenderArgs<T>& A, int64_t n_renders, bool carry) {
     if (n_renders > 0) {
-        if (A.plane_a || A.norm64) display_render_kernel<T, true><<<(unsigned)n_renders, 256, 0, ctx->stream>>>(A);
-        else display_render_kernel<T, false><<<(unsigned)n_renders, 256, 0, ctx->stream>>>(A);
+        if (A.plane_a || A.norm64) PSS_CUDA(ctx, pss_launch(display_render_kernel<T, true>, (unsigned)n_renders, 256u, 0, ctx->stream, A));
+        else PSS_CUDA(ctx, pss_launch(display_render_kernel<T, false>, (unsigned)n_renders, 256u, 0, ctx->stream, A));
         PSS_LAUNCH_CHECK(ctx);
     }
     if (carry && ring && ring->rows_max > 1) {

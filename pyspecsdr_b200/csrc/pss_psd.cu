@@ -550,6 +550,7 @@ psd_kernel(const PsdParams p) {
     bool rnan = false;
     __shared__ double mom_s[C::THREADS / 32][3];
 
+    pss_grid_dependency_sync();       // PSS_PDL: everything above touched only tables and this CTA's shared memory
     // ---- pass 0: global (coalesced 8-byte loads) * window -> radix-16 -> shared
     {
         cx<T> v[16];
@@ -1426,7 +1427,7 @@ static int launch_one(pss_ctx* ctx, const PsdParams& p) {
     PsdParams q = p;
     q.ahead = ctx->sm_count * ((EPI == EPI_SMOOTH && C::MINB == 2) ? pss_smooth_minb(LOG2N) : C::MINB);
     if (q.W > 1) q.col_step = (double)(C::N - 4 - 1) / (double)(q.W - 1);
-    kern<<<(unsigned)grid, C::THREADS, C::SMEM, ctx->stream>>>(q);
+    PSS_CUDA(ctx, pss_launch(kern, (unsigned)grid, (unsigned)C::THREADS, (size_t)C::SMEM, ctx->stream, q));
     PSS_LAUNCH_CHECK(ctx);
     return PSS_OK;
 }
