@@ -257,24 +257,27 @@ demod_force_kernel(const DecimDev D, const float2* __restrict__ iq, const int n_
 // any q; shared memory holds the response table only.  A warp works on U consecutive groups of 8 chunks at a
 // time and feeds every table fragment it loads to U tensor-core products: the kernel is bound by the
 // shared-memory / shuffle data path (ncu: 69 % of the LSU wavefront peak at U = 1), not by issue or the DMMA pipe.
-template <int SF, bool EDGE_CHECK, bool TAB_SMEM, int DIAG, int UNR, int U>
+template <int SF, bool EDGE_CHECK, bool TAB_SMEM, int DIAG, int UNR, int U, int PDX>
 __device__ __forceinline__ void force_unit_fused(const DecimDev& D, const float2* __restrict__ x, const int g0, const IqCorr kc,
                                                  const double* __restrict__ tab, const double* __restrict__ trow,
                                                  double (&c0)[U][(SF + 8) / 8], double (&c1)[U][(SF + 8) / 8],
                                                  double (&racc)[U], const int lane) {
     constexpr bool WFM = SF == 16;
-    constexpr int NTD = (SF + 8) / 8, PD = U == 1 ? 6 : 4;
+    constexpr int NTD = (SF + 8) / 8, PD = PDX ? PDX : (U == 1 ? 6 : 4);
     const int r = lane >> 2, c = lane & 3, KS = D.KS, N = D.N, L = D.N - 1;
     const int e0 = r * D.q + c, ustep = 8 * D.q;                      // group u starts 8 chunks further
     const float2* xp = x + g0 + e0;
     auto load = [&](int ks, int u) {
+        if (DIAG == 3) return make_float2(1.f + ks, 0.5f * lane);                   // DIAG 3: timing without the IQ loads
+        // (measured: clamping the index of the never-consumed k-steps beyond KS instead of predicating the load is 4 %
+        // slower, 0.633 vs 0.609 ms per GiB; widening the unchecked path's condition to the pipeline's whole reach
+        // and dropping the predicate 1.5 % slower -- more units take the checked path)
         bool ok = ks <= KS;
         if (EDGE_CHECK) {
             const int gi = g0 + u * ustep + e0 + 4 * ks;
             ok = ok && gi >= 0 && gi < N;
         }
         float2 v = make_float2(0.f, 0.f);
-        if (DIAG == 3) return make_float2(1.f + ks, 0.5f * lane);                   // DIAG 3: timing without the IQ loads
         if (ok) v = __ldg(xp + u * ustep + 4 * ks);
         return v;
     };
@@ -341,7 +344,7 @@ __device__ __forceinline__ void force_unit_fused(const DecimDev& D, const float2
     for (int u = 0; u < U; ++u) racc[u] += racc1[u];
 }
 
-template <int SF, bool TAB_SMEM, int DIAG = 0, int UNR = 4, int MINB = 3, int U = 1>
+template <int SF, bool TAB_SMEM, int DIAG = 0, int UNR = 6, int MINB = 3, int U = 1, int PDX = 0>
 __global__ void __launch_bounds__(FORCE_THREADS, MINB)
 demod_force_fused_kernel(const DecimDev D, const float2* __restrict__ iq, const int n_frames, double* __restrict__ F,
                          const float4* __restrict__ corr) {
@@ -381,9 +384,9 @@ demod_force_fused_kernel(const DecimDev D, const float2* __restrict__ iq, const 
             for (int nt = 0; nt < NTD; ++nt) c0[u][nt] = c1[u][nt] = 0.0;
         }
         if (g0 >= 0 && g0 + (8 * U - 1) * q + 4 * D.KS + 4 < D.N)
-            force_unit_fused<SF, false, TAB_SMEM, DIAG, UNR, U>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
+            force_unit_fused<SF, false, TAB_SMEM, DIAG, UNR, U, PDX>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
         else
-            force_unit_fused<SF, true, TAB_SMEM, DIAG, UNR, U>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
+            force_unit_fused<SF, true, TAB_SMEM, DIAG, UNR, U, PDX>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             double ra = racc[u];
@@ -817,6 +820,7 @@ static int launch_force(pss_ctx* ctx, pss_demod_plan* pl, const float2* iq, long
     const int tb = D.fused_tab_smem;
     static const int diag = getenv("PSS_DIAG") ? atoi(getenv("PSS_DIAG")) : 0;   // timing-only builds, wrong results
     static const int var = getenv("PSS_FORCE_VARIANT") ? atoi(getenv("PSS_FORCE_VARIANT")) : 0;   // tuning experiments
+    static const int unr = getenv("PSS_FORCE_UNR") ? atoi(getenv("PSS_FORCE_UNR")) : 0;           // 3, 4, 5, 7, 8, 9, 12
     if (tb && diag) {
         auto k = diag == 1 ? demod_force_fused_kernel<SF, true, 1> : diag == 2 ? demod_force_fused_kernel<SF, true, 2>
                  : diag == 3 ? demod_force_fused_kernel<SF, true, 3> : demod_force_fused_kernel<SF, true, 4>;
@@ -824,10 +828,32 @@ static int launch_force(pss_ctx* ctx, pss_demod_plan* pl, const float2* iq, long
         k<<<(unsigned)g1, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, F, corr);
     } else if (tb && var) {
         // 1: two groups per warp, 2 CTAs / SM;  2: two groups per warp, 3 CTAs / SM (80 registers)
-        auto k = var == 1 ? demod_force_fused_kernel<SF, true, 0, 3, 2, 2> : demod_force_fused_kernel<SF, true, 0, 3, 3, 2>;
+        // 3 / 4: the same with the loop unrolled by their pipeline depth (4)
+        auto k = var == 1 ? demod_force_fused_kernel<SF, true, 0, 3, 2, 2>
+                 : var == 3 ? demod_force_fused_kernel<SF, true, 0, 4, 2, 2>
+                 : var == 4 ? demod_force_fused_kernel<SF, true, 0, 4, 3, 2>
+                            : demod_force_fused_kernel<SF, true, 0, 3, 3, 2>;
         PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
-        long long gv = (var == 1 ? 2LL : 3LL) * ctx->sm_count;
+        long long gv = ((var == 1 || var == 3) ? 2LL : 3LL) * ctx->sm_count;
         k<<<(unsigned)gv, FORCE_THREADS, tb, ctx->stream>>>(D, iq, (int)nf, F, corr);
+    } else if (tb && unr) {
+        // Measured (same box, WFM demodulator per GiB): the k-step loop unrolled by the depth of the load pipeline
+        // (PD = 6: the register ring rotates by renaming, no moves) 0.608 ms -- the default; unrolled by 4 (the
+        // previous default, 13 register moves per 4 steps) 0.654; by 3: 0.661; by 12: 0.631; pipeline depth =
+        // unroll = 5 / 7 / 8 / 9: 0.651 / 0.643 / 0.623 / 0.639 (spills beyond 6 at 80 registers).
+        auto k = unr == 62 ? demod_force_fused_kernel<SF, true, 0, 6, 2, 1>          // 2 CTAs / SM at up to 128 registers
+                 : unr == 82 ? demod_force_fused_kernel<SF, true, 0, 8, 2, 1, 8>
+                 : unr == 102 ? demod_force_fused_kernel<SF, true, 0, 10, 2, 1, 10>
+                 : unr == 12 ? demod_force_fused_kernel<SF, true, 0, 12, 3, 1>
+                 : unr == 5 ? demod_force_fused_kernel<SF, true, 0, 5, 3, 1, 5>
+                 : unr == 7 ? demod_force_fused_kernel<SF, true, 0, 7, 3, 1, 7>
+                 : unr == 8 ? demod_force_fused_kernel<SF, true, 0, 8, 3, 1, 8>
+                 : unr == 9 ? demod_force_fused_kernel<SF, true, 0, 9, 3, 1, 9>
+                 : unr == 3 ? demod_force_fused_kernel<SF, true, 0, 3, 3, 1>
+                            : demod_force_fused_kernel<SF, true, 0, 4, 3, 1>;
+        PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
+        if (unr > 50 && g1 > 2LL * ctx->sm_count) g1 = 2LL * ctx->sm_count;
+        PSS_CUDA(ctx, pss_launch(k, (unsigned)g1, (unsigned)FORCE_THREADS, (size_t)tb, ctx->stream, D, iq, (int)nf, F, corr));
     } else if (tb) {
         auto k = demod_force_fused_kernel<SF, true>;
         PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
