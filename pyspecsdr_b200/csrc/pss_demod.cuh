@@ -24,6 +24,8 @@ struct DecimDev {
     float scale, norm;
     int tab_in_smem;
     int force_smem, scan_smem, fused_tab_smem;  // dynamic shared memory of the kernels (fused: 0 = table stays global)
+    const double* tabP;                         // packed fused-kernel table: [ks][pair][lane] double2 = (b0, b1), (b2 | r tap, r tap | 0)
+    int packed_tab_smem;
     long long slot_doubles;                     // doubles of scratch per block: rows * CS
     const double *tabF;                         // fragment-ordered body table [KS][NTD][32] then the r row [KS][4]
     const double *head, *tailT, *tailM;

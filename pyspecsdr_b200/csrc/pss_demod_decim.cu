@@ -257,7 +257,7 @@ demod_force_kernel(const DecimDev D, const float2* __restrict__ iq, const int n_
 // any q; shared memory holds the response table only.  A warp works on U consecutive groups of 8 chunks at a
 // time and feeds every table fragment it loads to U tensor-core products: the kernel is bound by the
 // shared-memory / shuffle data path (ncu: 69 % of the LSU wavefront peak at U = 1), not by issue or the DMMA pipe.
-template <int SF, bool EDGE_CHECK, bool TAB_SMEM, int DIAG, int UNR, int U, int PDX>
+template <int SF, bool EDGE_CHECK, bool TAB_SMEM, int DIAG, int UNR, int U, int PDX, bool PACK>
 __device__ __forceinline__ void force_unit_fused(const DecimDev& D, const float2* __restrict__ x, const int g0, const IqCorr kc,
                                                  const double* __restrict__ tab, const double* __restrict__ trow,
                                                  double (&c0)[U][(SF + 8) / 8], double (&c1)[U][(SF + 8) / 8],
@@ -322,10 +322,17 @@ __device__ __forceinline__ void force_unit_fused(const DecimDev& D, const float2
             av[u] = (double)d;
             S0[u] = S1;
         }
+        double bv[4];
+        if (PACK) {                  // two 16-byte loads per k-step: (b0, b1), (b2 | r tap, r tap | -)
+            const double2* pp = reinterpret_cast<const double2*>(tab) + (size_t)ks * 64 + lane;
+            const double2 p0 = TAB_SMEM ? pp[0] : __ldg(pp), p1 = TAB_SMEM ? pp[32] : __ldg(pp + 32);
+            bv[0] = p0.x, bv[1] = p0.y, bv[2] = p1.x, bv[3] = p1.y;
+        }
 #pragma unroll
         for (int nt = 0; nt < NTD; ++nt) {
             double b;
-            if (TAB_SMEM) b = bp[(ks * NTD + nt) * 32];
+            if (PACK) b = bv[nt];
+            else if (TAB_SMEM) b = bp[(ks * NTD + nt) * 32];
             else b = __ldg(bp + (ks * NTD + nt) * 32);
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -333,7 +340,7 @@ __device__ __forceinline__ void force_unit_fused(const DecimDev& D, const float2
                 else dmma_m8n8k4(c0[u][nt], c1[u][nt], av[u], b);
             }
         }
-        const double tr = TAB_SMEM ? tp[4 * ks] : __ldg(tp + 4 * ks);
+        const double tr = PACK ? bv[NTD] : (TAB_SMEM ? tp[4 * ks] : __ldg(tp + 4 * ks));
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             if (ks & 1) racc1[u] = fma(av[u], tr, racc1[u]);
@@ -344,7 +351,7 @@ __device__ __forceinline__ void force_unit_fused(const DecimDev& D, const float2
     for (int u = 0; u < U; ++u) racc[u] += racc1[u];
 }
 
-template <int SF, bool TAB_SMEM, int DIAG = 0, int UNR = 6, int MINB = 3, int U = 1, int PDX = 0>
+template <int SF, bool TAB_SMEM, int DIAG = 0, int UNR = 6, int MINB = 3, int U = 1, int PDX = 0, bool PACK = false>
 __global__ void __launch_bounds__(FORCE_THREADS, MINB)
 demod_force_fused_kernel(const DecimDev D, const float2* __restrict__ iq, const int n_frames, double* __restrict__ F,
                          const float4* __restrict__ corr) {
@@ -352,11 +359,12 @@ demod_force_fused_kernel(const DecimDev D, const float2* __restrict__ iq, const 
     constexpr int SB = 8, NTD = (SF + SB) / 8, RROW = SF + SB;
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double* tab = D.tabF;
+    const double* tab = PACK ? D.tabP : D.tabF;
     if (TAB_SMEM) {
         double* ts = reinterpret_cast<double*>(smem);
-        const int n = D.KS * (NTD * 32 + 4);
-        for (int i = tid; i < n; i += FORCE_THREADS) ts[i] = D.tabF[i];
+        const int n = PACK ? D.KS * 128 : D.KS * (NTD * 32 + 4);
+        const double* src = tab;
+        for (int i = tid; i < n; i += FORCE_THREADS) ts[i] = src[i];
         tab = ts;
         __syncthreads();
     }
@@ -384,9 +392,9 @@ demod_force_fused_kernel(const DecimDev D, const float2* __restrict__ iq, const 
             for (int nt = 0; nt < NTD; ++nt) c0[u][nt] = c1[u][nt] = 0.0;
         }
         if (g0 >= 0 && g0 + (8 * U - 1) * q + 4 * D.KS + 4 < D.N)
-            force_unit_fused<SF, false, TAB_SMEM, DIAG, UNR, U, PDX>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
+            force_unit_fused<SF, false, TAB_SMEM, DIAG, UNR, U, PDX, PACK>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
         else
-            force_unit_fused<SF, true, TAB_SMEM, DIAG, UNR, U, PDX>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
+            force_unit_fused<SF, true, TAB_SMEM, DIAG, UNR, U, PDX, PACK>(D, x, g0, kc, tab, trow, c0, c1, racc, lane);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             double ra = racc[u];
@@ -767,6 +775,20 @@ int pss_decim_create(pss_ctx* ctx, const pss_demod_desc* d, pss_demod_plan* pl) 
     const void* p;
     if ((rc = pss_demod_upload(ctx, pl, frag.data(), frag.size() * 8, &p))) return rc; D.tabF = (const double*)p;
     if ((rc = pss_demod_upload(ctx, pl, st.data(), st.size() * 8, &p))) return rc; D.scanTab = (const double*)p;
+    {   // the same fragments packed for 16-byte loads: per k-step two double2 per lane, (b0, b1) and (b2, r tap) [NTD = 3]
+        // or (r tap, 0) [NTD = 2]
+        std::vector<double> pk((size_t)D.KS * 2 * 32 * 2, 0.0);
+        for (int ks = 0; ks < D.KS; ++ks)
+            for (int l = 0; l < 32; ++l) {
+                double v[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int nt = 0; nt < D.NTD; ++nt) v[nt] = frag[((size_t)ks * D.NTD + nt) * 32 + l];
+                v[D.NTD] = frag[(size_t)D.KS * D.NTD * 32 + ks * 4 + (l & 3)];
+                for (int e = 0; e < 4; ++e) pk[(((size_t)ks * 2 + e / 2) * 32 + l) * 2 + (e & 1)] = v[e];
+            }
+        if ((rc = pss_demod_upload(ctx, pl, pk.data(), pk.size() * 8, &p))) return rc;
+        D.tabP = (const double*)p;
+        D.packed_tab_smem = pk.size() * 8 <= 72 * 1024 ? (int)(pk.size() * 8) : 0;
+    }
     if ((rc = pss_demod_upload(ctx, pl, d->head, (size_t)(D.SF + 1) * (EDGE + 1) * 8, &p))) return rc; D.head = (const double*)p;
     if ((rc = pss_demod_upload(ctx, pl, d->tail_T, (size_t)(D.SB + D.m_tail) * D.tail_len * 8, &p))) return rc; D.tailT = (const double*)p;
     if ((rc = pss_demod_upload(ctx, pl, d->tail_M, (size_t)(D.SB + D.m_tail) * D.SF * 8, &p))) return rc; D.tailM = (const double*)p;
@@ -820,6 +842,7 @@ static int launch_force(pss_ctx* ctx, pss_demod_plan* pl, const float2* iq, long
     const int tb = D.fused_tab_smem;
     static const int diag = getenv("PSS_DIAG") ? atoi(getenv("PSS_DIAG")) : 0;   // timing-only builds, wrong results
     static const int var = getenv("PSS_FORCE_VARIANT") ? atoi(getenv("PSS_FORCE_VARIANT")) : 0;   // tuning experiments
+    static const int pack = getenv("PSS_FORCE_PACK") ? atoi(getenv("PSS_FORCE_PACK")) : 0;       // packed table, 16-byte loads
     static const int unr = getenv("PSS_FORCE_UNR") ? atoi(getenv("PSS_FORCE_UNR")) : 0;           // 3, 4, 5, 7, 8, 9, 12
     if (tb && diag) {
         auto k = diag == 1 ? demod_force_fused_kernel<SF, true, 1> : diag == 2 ? demod_force_fused_kernel<SF, true, 2>
@@ -854,6 +877,10 @@ static int launch_force(pss_ctx* ctx, pss_demod_plan* pl, const float2* iq, long
         PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
         if (unr > 50 && g1 > 2LL * ctx->sm_count) g1 = 2LL * ctx->sm_count;
         PSS_CUDA(ctx, pss_launch(k, (unsigned)g1, (unsigned)FORCE_THREADS, (size_t)tb, ctx->stream, D, iq, (int)nf, F, corr));
+    } else if (tb && pack && D.packed_tab_smem) {
+        auto k = demod_force_fused_kernel<SF, true, 0, 6, 3, 1, 0, true>;
+        PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, D.packed_tab_smem));
+        PSS_CUDA(ctx, pss_launch(k, (unsigned)g1, (unsigned)FORCE_THREADS, (size_t)D.packed_tab_smem, ctx->stream, D, iq, (int)nf, F, corr));
     } else if (tb) {
         auto k = demod_force_fused_kernel<SF, true>;
         PSS_CUDA(ctx, cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, tb));
