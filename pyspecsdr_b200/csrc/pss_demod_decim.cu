@@ -510,12 +510,19 @@ demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __rest
     double* Fs = reinterpret_cast<double*>(bar + 2);                  // [rows][CS] (SLOT_SMEM)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const ScanTabLayout T{NF, NBK};
-    for (int i = tid; i < D.scan_tab_doubles; i += SCAN_THREADS) tabs[i] = D.scanTab[i];
+    auto issue_slot_copy = [&](const int frame) {       // one thread: the block's forcing rows -> shared memory (TMA bulk copies)
+        const unsigned bytes = (unsigned)(D.slot_doubles * 8);
+        mbar_expect_tx(bar, bytes);
+        const char* src = reinterpret_cast<const char*>(F + (long long)frame * D.slot_doubles);
+        for (unsigned o = 0; o < bytes; o += 32768u)              // bulk copies of <= 32 KB
+            bulk_g2s(reinterpret_cast<char*>(Fs) + o, src + o, min(32768u, bytes - o), bar);
+    };
+    pss_grid_dependency_sync();       // PSS_PDL: the forcing rows belong to the previous kernel
     if (SLOT_SMEM && tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((int)blockIdx.x < n_frames) issue_slot_copy(blockIdx.x);   // the first block's copy runs beside the table copy
     }
-    pss_grid_dependency_sync();       // PSS_PDL: tables copied, barrier initialised; the forcing rows belong to the previous kernel
     unsigned phase = 0;
     const double *Gm = tabs + T.G(), *CR = tabs + T.CR(), *CB = tabs + T.CB();
     const double *BF = tabs + T.BF(), *PWF = tabs + T.PWF(), *BBk = tabs + T.BB(), *PWB = tabs + T.PWB();
@@ -525,13 +532,7 @@ demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __rest
         const float2* x = iq + (long long)frame * D.N;
         double* Fb = SLOT_SMEM ? Fs : F + (long long)frame * D.slot_doubles;
         __syncthreads();                                              // the previous block is done with Fs / bar
-        if (SLOT_SMEM && tid == 0) {
-            const unsigned bytes = (unsigned)(D.slot_doubles * 8);
-            mbar_expect_tx(bar, bytes);
-            const char* src = reinterpret_cast<const char*>(F + (long long)frame * D.slot_doubles);
-            for (unsigned o = 0; o < bytes; o += 32768u)              // bulk copies of <= 32 KB
-                bulk_g2s(reinterpret_cast<char*>(Fs) + o, src + o, min(32768u, bytes - o), bar);
-        }
+        if (SLOT_SMEM && tid == 0 && frame != (int)blockIdx.x) issue_slot_copy(frame);
         IqCorr kc = {1.f, 1.f, 0.f, 1.f};
         if (WFM && D.iq_correct) {
             const float4 c = __ldg(corr + frame);
@@ -540,6 +541,8 @@ demod_scan_kernel(const DecimDev D, const float2* __restrict__ iq, float* __rest
         // ---- head: ext[0..27] depends on d[0..27] only; tail window
         if (tid <= EDGE) dh[tid] = (double)discriminator<WFM>(x, tid, L, kc, D.scale);
         for (int i = tid; i < D.tail_len; i += SCAN_THREADS) tile[i] = discriminator<WFM>(x, D.tail_start + i, L, kc, D.scale);
+        if (frame == (int)blockIdx.x)             // the scan tables: first needed after this barrier
+            for (int i = tid; i < D.scan_tab_doubles; i += SCAN_THREADS) tabs[i] = D.scanTab[i];
         __syncthreads();
         if (tid <= SF) {
             double acc = 0.0;

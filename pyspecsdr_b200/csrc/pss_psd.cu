@@ -123,6 +123,84 @@ __device__ __forceinline__ void hist_pick_wide(const unsigned* h, unsigned& rank
 }
 
 
+// Rare path of the epilogue's median (crowded bucket: flat rows): 4 x 8-bit radix select on order-preserving
+// keys normalised to the occupied key range.  A real call, so that its ~1000 instructions stay out of the hot
+// code (the fused kernel is ~60 KB of SASS and its speed moves by 3 % with its placement in the instruction
+// cache); it re-reads the thread's 16 smoothed values from shared memory instead of taking them in registers.
+// Called by every thread of the CTA (all frames); hist [1024], uf [8] ([0] = [3] = 0xffffffff, rest 0 on entry).
+template <int N, int TPF>
+__device__ __noinline__ void rare_median(const float* __restrict__ srow, unsigned* hist, unsigned* uf, const int t,
+                                         float& v1, float& v2) {
+    constexpr int n = N - 4;
+    const int lane = t & 31;
+    unsigned key[16];
+    bool gvalid[4];
+    unsigned kmin = 0xffffffffu, kmax = 0u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i0 = 4 * t + 4 * TPF * q;
+        gvalid[q] = i0 < n;
+        const float4 v = *reinterpret_cast<const float4*>(srow + i0);
+        key[4 * q] = f2key(v.x);
+        key[4 * q + 1] = f2key(v.y);
+        key[4 * q + 2] = f2key(v.z);
+        key[4 * q + 3] = f2key(v.w);
+        if (gvalid[q]) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                kmin = min(kmin, key[4 * q + e]);
+                kmax = max(kmax, key[4 * q + e]);
+            }
+        }
+    }
+    for (int b = t; b < 1024; b += TPF) hist[b] = 0u;
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    if (lane == 0) {
+        atomicMin(&uf[0], kmin);
+        atomicMax(&uf[1], kmax);
+    }
+    __syncthreads();
+    kmin = uf[0];
+    kmax = uf[1];
+    const int common = min(__clz((int)(kmin ^ kmax)), 31);
+#pragma unroll
+    for (int m2 = 0; m2 < 16; ++m2) key[m2] = (key[m2] - kmin) << common;
+    unsigned rk = (unsigned)((n - 1) / 2), prefix = 0u, dg, cnt;
+#pragma unroll
+    for (int ps = 0; ps < 4; ++ps) {
+        const int shift = 24 - 8 * ps;
+        unsigned* h = hist + ps * 256;
+#pragma unroll
+        for (int m2 = 0; m2 < 16; ++m2) {
+            const bool match = ps == 0 ? true : (key[m2] >> (shift + 8)) == prefix;
+            if (gvalid[m2 >> 2] && match) atomicAdd(&h[(key[m2] >> shift) & 255u], 1u);
+        }
+        __syncthreads();
+        hist_pick(h, rk, dg, cnt, lane);
+        prefix = (prefix << 8) | dg;
+    }
+    const unsigned key1n = prefix;                   // normalised key of the lower median
+    unsigned cnt_le = 0, min_gt = 0xffffffffu;
+#pragma unroll
+    for (int m2 = 0; m2 < 16; ++m2) {
+        if (gvalid[m2 >> 2]) {
+            cnt_le += key[m2] <= key1n;
+            if (key[m2] > key1n) min_gt = min(min_gt, key[m2]);
+        }
+    }
+    cnt_le = __reduce_add_sync(0xffffffffu, cnt_le);
+    min_gt = __reduce_min_sync(0xffffffffu, min_gt);
+    if (lane == 0) {
+        atomicAdd(&uf[2], cnt_le);
+        atomicMin(&uf[3], min_gt);
+    }
+    __syncthreads();
+    const unsigned key2n = ((n & 1) || uf[2] > (unsigned)(n / 2)) ? key1n : uf[3];
+    v1 = key2f((key1n >> common) + kmin);
+    v2 = key2f((key2n >> common) + kmin);
+}
+
 // The main-loop epilogue on one dB row held in shared memory (pyspecsdr.py:2278-2283, 388-389, and the
 // W-column np.interp resample of the draw_* functions): 5-bin 'valid' mean, exact median - 10 dB clamp, row
 // statistics, stores.  Called by every thread of the frame's group of TPF = N/16 threads; `row` [N] raw dB
@@ -309,64 +387,8 @@ __device__ __forceinline__ void smooth_epilogue(const float* __restrict__ row, f
             v1 = __uint_as_float(us[4]);
             v2 = (n & 1) ? v1 : (rank + 1u < m ? __uint_as_float(us[5]) : key2f(us[3]));
         } else {
-            // ---- rare path (a frame of this CTA has > CAP equal-bucket elements): 4 x 8-bit radix select
-            // on order-preserving keys normalised to the occupied key range; every frame of the CTA runs it
-            unsigned key[16];
-            unsigned kmin = 0xffffffffu, kmax = 0u;
-#pragma unroll
-            for (int m2 = 0; m2 < 16; ++m2) {
-                key[m2] = f2key(s[m2]);
-                if (gvalid[m2 >> 2]) {
-                    kmin = min(kmin, key[m2]);
-                    kmax = max(kmax, key[m2]);
-                }
-            }
-            for (int b = t; b < 1024; b += TPF) hist[b] = 0u;
-            kmin = __reduce_min_sync(0xffffffffu, kmin);
-            kmax = __reduce_max_sync(0xffffffffu, kmax);
-            if (lane == 0) {
-                atomicMin(&uf[0], kmin);
-                atomicMax(&uf[1], kmax);
-            }
-            __syncthreads();
-            kmin = uf[0];
-            kmax = uf[1];
-            const int common = min(__clz((int)(kmin ^ kmax)), 31);
-#pragma unroll
-            for (int m2 = 0; m2 < 16; ++m2) key[m2] = (key[m2] - kmin) << common;
-            unsigned rk = (unsigned)((n - 1) / 2), prefix = 0u, dg, cnt;
-#pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                const int shift = 24 - 8 * ps;
-                unsigned* h = hist + ps * 256;
-#pragma unroll
-                for (int m2 = 0; m2 < 16; ++m2) {
-                    const bool match = ps == 0 ? true : (key[m2] >> (shift + 8)) == prefix;
-                    if (gvalid[m2 >> 2] && match) atomicAdd(&h[(key[m2] >> shift) & 255u], 1u);
-                }
-                __syncthreads();
-                hist_pick(h, rk, dg, cnt, lane);
-                prefix = (prefix << 8) | dg;
-            }
-            const unsigned key1n = prefix;                   // normalised key of the lower median
-            unsigned cnt_le = 0, min_gt = 0xffffffffu;
-#pragma unroll
-            for (int m2 = 0; m2 < 16; ++m2) {
-                if (gvalid[m2 >> 2]) {
-                    cnt_le += key[m2] <= key1n;
-                    if (key[m2] > key1n) min_gt = min(min_gt, key[m2]);
-                }
-            }
-            cnt_le = __reduce_add_sync(0xffffffffu, cnt_le);
-            min_gt = __reduce_min_sync(0xffffffffu, min_gt);
-            if (lane == 0) {
-                atomicAdd(&uf[2], cnt_le);
-                atomicMin(&uf[3], min_gt);
-            }
-            __syncthreads();
-            const unsigned key2n = ((n & 1) || uf[2] > (unsigned)(n / 2)) ? key1n : uf[3];
-            v1 = key2f((key1n >> common) + kmin);
-            v2 = key2f((key2n >> common) + kmin);
+            // ---- rare path (a frame of this CTA has > CAP equal-bucket elements); every frame of the CTA runs it
+            rare_median<N, TPF>(srow, hist, uf, t, v1, v2);
         }
         float thr = (float)(0.5 * ((double)v1 + (double)v2) - 10.0);
         const bool any_nan = us[6] != 0u;
