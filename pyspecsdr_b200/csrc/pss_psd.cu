@@ -15,6 +15,15 @@
 #include "pss_fft.cuh"
 
 enum { EPI_RAW = 0, EPI_SMOOTH = 1, EPI_SCAN = 2 };
+// Threads per CTA of the small transforms: one frame per CTA down to one warp (N = 512), several frames per
+// warp-CTA below.  Until late in round 2 every CTA had 256 threads (4 frames of 1024 points, 8 of 512): the same
+// warps per SM, but every barrier then waits for 8 warps instead of 1, 2 or 4.  Same box, ms per GiB, raw /
+// smoothing / scanner: 512: 0.528 / 1.012 / 0.616 -> 0.456 / 0.866 / 0.517; 1024: 0.519 / 0.891 / 0.632 ->
+// 0.440 / 0.818 / 0.527; 2048: 0.537 / 0.874 / 0.641 -> 0.479 / 0.785 / 0.558 (-DPSS_PSD_MIN_THREADS=256|128|64
+// rebuilds the other points of the comparison).
+#ifndef PSS_PSD_MIN_THREADS
+#define PSS_PSD_MIN_THREADS 32
+#endif
 // CTAs per SM the smoothing variant's 64 KB configurations are compiled for (-DPSS_SMOOTH_MINB=n overrides)
 #ifdef PSS_SMOOTH_MINB
 constexpr int pss_smooth_minb(int) { return PSS_SMOOTH_MINB; }
@@ -45,9 +54,10 @@ template <int LOG2N, typename T>
 struct PsdCfg {
     static constexpr int N = 1 << LOG2N;
     static constexpr int TPF = N / 16;                       // threads per frame
-    static constexpr int THREADS = TPF > 256 ? TPF : 256;
+    static constexpr int THREADS = TPF > PSS_PSD_MIN_THREADS ? TPF : PSS_PSD_MIN_THREADS;
     static constexpr int FPC = THREADS / TPF;                // frames per CTA
-    static constexpr int MINB = (sizeof(T) * 2 * N * FPC <= 32 * 1024) ? 4 : (sizeof(T) * 2 * N * FPC <= 64 * 1024) ? 2 : 1;
+    // ~120 registers per thread: 512 threads per SM whatever the CTA size; shared memory scales with the threads
+    static constexpr int MINB = (sizeof(T) * 2 * N * FPC > 64 * 1024) ? 1 : (512 / THREADS < 1 ? 1 : 512 / THREADS);
     static constexpr size_t SMEM = (size_t)FPC * N * sizeof(cx<T>);
     static constexpr int NP = pss_num_passes(LOG2N);
     static constexpr int CAP = TPF < 64 ? TPF : 64;          // median candidates ranked directly (EPI_SMOOTH)
