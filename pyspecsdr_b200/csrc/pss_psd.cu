@@ -24,11 +24,11 @@ enum { EPI_RAW = 0, EPI_SMOOTH = 1, EPI_SCAN = 2 };
 #ifndef PSS_PSD_MIN_THREADS
 #define PSS_PSD_MIN_THREADS 32
 #endif
-// CTAs per SM the smoothing variant's 64 KB configurations are compiled for (-DPSS_SMOOTH_MINB=n overrides)
+// CTAs per SM the 4096-point smoothing variant is compiled for (-DPSS_SMOOTH_MINB=n overrides)
 #ifdef PSS_SMOOTH_MINB
 constexpr int pss_smooth_minb(int) { return PSS_SMOOTH_MINB; }
 #else
-constexpr int pss_smooth_minb(int log2n) { return log2n <= 10 ? 3 : 2; }
+constexpr int pss_smooth_minb(int) { return 2; }
 #endif
 
 struct PsdParams {
@@ -530,11 +530,12 @@ __device__ __forceinline__ void stockham_pass(cx<T>* __restrict__ buf, const cx<
 // LOG2N1 > 0: this launch is the second stage of a length N*2^LOG2N1 transform (four-step FFT): frame
 // index = big_frame * N1 + k1, input = column-transformed, twiddled fp64 rows, output bin = k1 + N1*k2.
 template <int LOG2N, typename T, int EPI, int LOG2N1 = 0>
-// Occupancy of the 64 KB-per-CTA configurations: 2 CTAs/SM at ~110-120 registers for the raw / scanner
-// variants.  The smoothing variant went back and forth with its median: 3 CTAs/SM at 80 registers with the
-// 13-barrier key radix select, 2 CTAs/SM (+6 %) with the 6-barrier two-level histogram, and 3 CTAs/SM again
-// (+2.5 % at 4096 points, +3 % at 1024, -2 % at 2048: pss_smooth_minb) with the 5-barrier single-histogram
-// median below; `tools/build_variant.sh minb2 -DPSS_SMOOTH_MINB=2` rebuilds the other side of the comparison.
+// Occupancy: ~120 registers per thread, i.e. 512 threads per SM whatever the CTA size (PsdCfg::MINB).  The
+// 4096-point smoothing variant (the only 2-CTA configuration left since the small transforms run one frame per
+// CTA) went back and forth with its median: 3 CTAs/SM at 80 registers with the 13-barrier key radix select,
+// 2 CTAs/SM (+6 %) with the 6-barrier two-level histogram, 3 again (+2.5 %) with the first single-histogram
+// version, and 2 (+2.7 %) once one warp scans the histogram; `tools/build_variant.sh minb3 -DPSS_SMOOTH_MINB=3`
+// rebuilds the other side of the comparison.
 __global__ void __launch_bounds__(PsdCfg<LOG2N, T>::THREADS,
                                   (EPI == EPI_SMOOTH && PsdCfg<LOG2N, T>::MINB == 2) ? pss_smooth_minb(LOG2N) : PsdCfg<LOG2N, T>::MINB)
 psd_kernel(const PsdParams p) {
