@@ -7,7 +7,9 @@
 
 #define EDGE 27
 #define FORCE_THREADS 256        // forcing kernel: 8 independent warps per CTA
-#define SCAN_THREADS 256         // scan kernel: one CTA of 8 warps per block of audio
+#ifndef SCAN_THREADS
+#define SCAN_THREADS 256         // scan kernel: one CTA of 8 warps per block of audio (-DSCAN_THREADS=128: 4 warps, same 3 CTAs/SM -- measured +3 % on the demodulator)
+#endif
 #define SCAN_CPL 10              // chunks per lane of the scan kernel (32 * SCAN_CPL chunks per segment)
 #define WBUF_FLOATS 1088         // per-warp discriminator window of the forcing kernel
 #define SLAB_ROW 132             // row stride of the 8-row slab layout (== 4 mod 8: conflict-free A fragments)
