@@ -21,8 +21,9 @@ def rows_for(rng, n, count):
             r[rng.integers(0, n)] += rng.uniform(10, 80)           # a carrier
         if s and rng.random() < 0.15:
             r = out[-1].copy()                                     # a repeated row
-        if rng.random() < 0.1:
-            r = np.round(r, 1)                                     # many ties, values on round numbers
+        if rng.random() < 0.1 and spread > 1.0:
+            r = np.round(r, 1)                                     # many ties, values on round numbers (never a
+                                                                   # constant stack: the reference's int(nan) raises there)
         out.append(r)
     return out
 
