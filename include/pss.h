@@ -218,8 +218,9 @@ int  pss_demod_c64_dev_moments(pss_ctx* ctx, pss_demod_plan* plan, const float* 
  * owns any number of display streams, each a ring of the last rows_max - 1 rows (their W-column resample and
  * finite min/max) carried on the device across calls, so N calls of one row are bitwise one call of N rows.
  *   pss_display_open(ctx, stream, kind, W, rows_max, H)   create / reset stream `stream` (any int id)
- *        kind = PSS_QUANT_*: WATERFALL divides by max-min as is; GRADIENT / PERSISTENCE / SURFACE replace a
- *        zero range by 1 (:1528-1530, :1657-1659, :1577-1579).  H = display_height (PERSISTENCE only).
+ *        kind = PSS_QUANT_*: WATERFALL divides by max-min as is (a constant stack gives NaN values and plane
+ *        cells 255 = nothing drawn: the reference's int(nan) raises there and the frame is not drawn);
+ *        GRADIENT / PERSISTENCE / SURFACE replace a zero range by 1 (:1528-1530, :1657-1659, :1577-1579).  H = display_height (PERSISTENCE only).
  *        SURFACE has no history (rows_max must be 1).
  *   pss_display_accumulate_f64   HOST fp64 dB rows [n_rows][n_bins], one render after every row (the call
  *        pattern of the draw_* functions).  Everything is fp64 in numpy's operation order with no fused
