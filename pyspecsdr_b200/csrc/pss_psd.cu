@@ -1459,6 +1459,10 @@ static int launch_one(pss_ctx* ctx, const PsdParams& p) {
     const long long grid = (p.n_frames + C::FPC - 1) / C::FPC;
     PsdParams q = p;
     q.ahead = ctx->sm_count * ((EPI == EPI_SMOOTH && C::MINB == 2) ? pss_smooth_minb(LOG2N) : C::MINB);
+    {   // PSS_PSD_AHEAD=<percent of the resident CTAs> (tuning): 0 switches the L2 prefetch-ahead off
+        static const int pct = getenv("PSS_PSD_AHEAD") ? atoi(getenv("PSS_PSD_AHEAD")) : 100;
+        q.ahead = (int)((long long)q.ahead * pct / 100);
+    }
     if (q.W > 1) q.col_step = (double)(C::N - 4 - 1) / (double)(q.W - 1);
     PSS_CUDA(ctx, pss_launch(kern, (unsigned)grid, (unsigned)C::THREADS, (size_t)C::SMEM, ctx->stream, q));
     PSS_LAUNCH_CHECK(ctx);
